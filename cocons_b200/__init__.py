@@ -1,0 +1,30 @@
+"""cocons_b200 - B200-native dense-likelihood path of blasif/cocons.
+
+The product is libcocons_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/cocons_b200.h).  This package is its host-side mirror of the
+reference's R interface; see api.py.
+"""
+from .api import (  # noqa: F401
+    CoconsError,
+    DenseLikelihood,
+    GetNeg2loglikelihood,
+    GetNeg2loglikelihoodProfile,
+    GetNeg2loglikelihoodREML,
+    NotPositiveDefinite,
+    coco,
+    cocoOptim,
+    cocoPredict,
+    cocoSim,
+    cov_rns,
+    cov_rns_classic,
+    cov_rns_pred,
+    getCovMatrix,
+    getDesignMatrix,
+    getModelLists,
+    getScale,
+    is_formula,
+    reml_contrasts,
+    sumsmoothlone,
+)
+
+__version__ = "0.1.0"

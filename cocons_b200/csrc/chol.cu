@@ -1,0 +1,313 @@
+// Blocked right-looking Cholesky on the device (FP64), replacing the LAPACK
+// dpotrf behind base::chol at R/neg2loglikelihood.R:136,200,259, R/sim.R:106,162
+// and R/optim.R:336.  Lower factor, in place on a column-major matrix padded to
+// a multiple of 128 (identity in the padding).
+//
+//   potrf_tile_kernel   K3: 128x128 diagonal tile, factor + explicit inverse
+//   gemm_nt_kernel      K4/K5: C (-)= A B^T on FP64 tensor cores (DMMA.8x8x4 via
+//                       mma.sync.m8n8k4.f64), operands streamed global->shared by
+//                       the async copy engine; used for the panel solve
+//                       (X = A inv(L_jj)^T), the in-panel update and the trailing
+//                       SYRK update
+//   chol_factor         two-level driver: 128-wide steps inside 512-wide panels
+#include <algorithm>
+
+#include "../../include/cocons_b200.h"
+#include "common.cuh"
+
+namespace cocons {
+
+// ---------------------------------------------------------------------------
+// DMMA NT GEMM.  C[M x N] (-)= A[M x K] * B[N x K]^T, everything column-major,
+// M, N multiples of 128, K a multiple of 16.
+//
+// CTA tile 128(i) x 128(j), 8 warps as 2(i) x 4(j), warp tile 64(i) x 32(j).
+// The mma's M dimension runs over matrix COLUMNS j and its N dimension over
+// matrix ROWS i, so that the two accumulator registers of a thread are two
+// consecutive rows of one column; with fragment row g of the tile pair
+// (2u, 2u+1) bound to matrix rows {2g, 2g+1} + 16u a thread ends up owning 4
+// consecutive rows (32 B) and a quad 128 contiguous bytes of a column.  The
+// same binding makes every operand fetch one conflict-free LDS.128.
+// ---------------------------------------------------------------------------
+constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 4;
+constexpr int GLDS = 132;  // padded leading dimension of a shared k-row (== 4 mod 16)
+constexpr int kGemmSmemBytes = GSTAGES * 2 * GBK * GLDS * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// tile index -> (bi, bj) of a lower trapezoid with ni >= nj tile rows/cols, column by column
+__device__ __forceinline__ void trapezoid_decode(int64_t t, int ni, int& bi, int& bj) {
+  // tiles before column c: S(c) = c*ni - c(c-1)/2
+  const double b = (double)ni + 0.5;
+  int c = (int)(b - sqrt(b * b - 2.0 * (double)t));
+  if (c < 0) c = 0;
+  while ((int64_t)(c + 1) * ni - (int64_t)(c + 1) * c / 2 <= t) ++c;
+  while ((int64_t)c * ni - (int64_t)c * (c - 1) / 2 > t) --c;
+  bj = c;
+  bi = c + (int)(t - ((int64_t)c * ni - (int64_t)c * (c - 1) / 2));
+}
+
+template <int ASSIGN>
+__global__ void __launch_bounds__(256, 1)
+    gemm_nt_kernel(int ni, int nj, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                   int64_t ldc, int lower_only) {
+  extern __shared__ __align__(16) double smem[];
+  int bi, bj;
+  if (lower_only) {
+    trapezoid_decode(blockIdx.x, ni, bi, bj);
+  } else {
+    bj = blockIdx.x / ni;
+    bi = blockIdx.x - bj * ni;
+  }
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c4 = lane & 3;
+  const int iw = (warp & 1) * 64, jw = (warp >> 1) * 32;
+  const double* Ag = A + (int64_t)bi * GBM;
+  const double* Bg = B + (int64_t)bj * GBN;
+
+  auto As = [&](int s) { return smem + (size_t)s * (2 * GBK * GLDS); };
+  auto Bs = [&](int s) { return smem + (size_t)s * (2 * GBK * GLDS) + GBK * GLDS; };
+
+  auto load_stage = [&](int s, int64_t kb) {
+    double* as = As(s);
+    double* bs = Bs(s);
+#pragma unroll
+    for (int c = tid; c < GBK * (GBM / 2); c += 256) {
+      const int k = c >> 6, i2 = c & 63;
+      cp_async16(as + k * GLDS + 2 * i2, Ag + (kb * GBK + k) * lda + 2 * i2);
+      cp_async16(bs + k * GLDS + 2 * i2, Bg + (kb * GBK + k) * ldb + 2 * i2);
+    }
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  const int64_t nkb = K / GBK;
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nkb) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int64_t kb = 0; kb < nkb; ++kb) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    {
+      const int64_t nxt = kb + GSTAGES - 1;
+      if (nxt < nkb) load_stage((int)(nxt % GSTAGES), nxt);
+      cp_async_commit();
+    }
+    const double* as = As((int)(kb % GSTAGES)) + iw + 2 * g;
+    const double* bs = Bs((int)(kb % GSTAGES)) + jw + 2 * g;
+#pragma unroll
+    for (int kk = 0; kk < GBK / 4; ++kk) {
+      const int k = kk * 4 + c4;
+      double fi[8], fj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2 v = *reinterpret_cast<const double2*>(as + k * GLDS + 16 * u);
+        fi[2 * u] = v.x;
+        fi[2 * u + 1] = v.y;
+      }
+#pragma unroll
+      for (int v2 = 0; v2 < 2; ++v2) {
+        const double2 v = *reinterpret_cast<const double2*>(bs + k * GLDS + 16 * v2);
+        fj[2 * v2] = v.x;
+        fj[2 * v2 + 1] = v.y;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: a thread owns rows r0..r0+3 of column j for every (a, u)
+  double* Cg = C + (int64_t)bj * GBN * ldc + (int64_t)bi * GBM;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int j = jw + 16 * (a >> 1) + 2 * g + (a & 1);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r0 = iw + 16 * u + 4 * c4;
+      double2* p = reinterpret_cast<double2*>(Cg + (int64_t)j * ldc + r0);
+      double2 lo, hi;
+      if (ASSIGN) {
+        lo.x = acc[a][2 * u][0];
+        lo.y = acc[a][2 * u + 1][0];
+        hi.x = acc[a][2 * u][1];
+        hi.y = acc[a][2 * u + 1][1];
+      } else {
+        lo = p[0];
+        hi = p[1];
+        lo.x -= acc[a][2 * u][0];
+        lo.y -= acc[a][2 * u + 1][0];
+        hi.x -= acc[a][2 * u][1];
+        hi.y -= acc[a][2 * u + 1][1];
+      }
+      p[0] = lo;
+      p[1] = hi;
+    }
+  }
+}
+
+void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                    int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    attr_done = true;
+  }
+  const int ni = (int)(M / GBM), nj = (int)(N / GBN);
+  int64_t tiles = lower_only ? ((int64_t)nj * ni - (int64_t)nj * (nj - 1) / 2) : (int64_t)ni * nj;
+  note_launch();
+  if (mode == 1)
+    gemm_nt_kernel<1><<<(unsigned)tiles, 256, kGemmSmemBytes, st>>>(ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+  else
+    gemm_nt_kernel<0><<<(unsigned)tiles, 256, kGemmSmemBytes, st>>>(ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+}
+
+// ---------------------------------------------------------------------------
+// Diagonal tile: unblocked Cholesky of a 128 x 128 tile held in shared memory,
+// followed by the explicit inverse W = L^-1 (lower triangular), which turns the
+// panel solve and the later forward substitutions into plain products.
+// Shared layout: L(i,j), j <= i, at S[i][j]; W(r,c), c <= r, at S[c][r+1]
+// (the otherwise unused strict upper part), row stride 129 doubles.
+// ---------------------------------------------------------------------------
+constexpr int PT = kTile;
+constexpr int PLD = PT + 1;
+constexpr int kPotrfSmemBytes = PT * PLD * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+    potrf_tile_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int* __restrict__ info,
+                      int first_index) {
+  extern __shared__ __align__(16) double S[];
+  __shared__ double red[256];
+  __shared__ int fail;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) fail = 0;
+  // load the lower triangle (column-major global, coalesced along i)
+  for (int idx = tid; idx < PT * PT; idx += 256) {
+    const int j = idx >> 7, i = idx & (PT - 1);
+    if (i >= j) S[i * PLD + j] = A[(int64_t)j * ld + i];
+  }
+  __syncthreads();
+  for (int k = 0; k < PT; ++k) {
+    const double d = S[k * PLD + k];
+    if (!(d > 0.0)) {  // non-positive or NaN pivot: dpotrf's info = k+1
+      if (tid == 0) {
+        fail = 1;
+        atomicCAS(info, 0, first_index + k + 1);
+      }
+      break;
+    }
+    const double piv = sqrt(d);
+    __syncthreads();  // everyone has read the pivot
+    if (tid == 0) S[k * PLD + k] = piv;
+    for (int i = k + 1 + tid; i < PT; i += 256) S[i * PLD + k] = S[i * PLD + k] / piv;
+    __syncthreads();
+    // trailing update: warp per column j, lanes over rows i >= j
+    for (int j = k + 1 + warp; j < PT; j += 8) {
+      const double ljk = S[j * PLD + k];
+      for (int i = j + lane; i < PT; i += 32) S[i * PLD + j] = fma(-S[i * PLD + k], ljk, S[i * PLD + j]);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (fail) return;
+  // write L back (lower part; the strict upper part of the tile is zeroed)
+  for (int idx = tid; idx < PT * PT; idx += 256) {
+    const int j = idx >> 7, i = idx & (PT - 1);
+    A[(int64_t)j * ld + i] = (i >= j) ? S[i * PLD + j] : 0.0;
+  }
+  // W = L^-1 by rows: W[r][c] = (delta_rc - sum_{k=c}^{r-1} L[r][k] W[k][c]) / L[r][r]
+  // thread (c, h): column c = tid & 127, half h = tid >> 7 of the k range
+  const int c = tid & (PT - 1), h = tid >> 7;
+  for (int r = 0; r < PT; ++r) {
+    double part = 0.0;
+    if (c < r) {
+      const int len = r - c;
+      const int kbeg = c + (h ? (len + 1) / 2 : 0);
+      const int kend = h ? r : c + (len + 1) / 2;
+      for (int k = kbeg; k < kend; ++k) part = fma(S[r * PLD + k], S[c * PLD + k + 1], part);
+    }
+    red[tid] = part;
+    __syncthreads();
+    if (h == 0 && c <= r) {
+      const double s = red[c] + red[c + PT];
+      const double rhs = (c == r) ? 1.0 : 0.0;
+      S[c * PLD + r + 1] = (rhs - s) / S[r * PLD + r];
+    }
+    __syncthreads();
+  }
+  // Winv: 128 x 128 column-major, element (row c_, col k_) = W[c_][k_], zero above the diagonal
+  for (int idx = tid; idx < PT * PT; idx += 256) {
+    const int kcol = idx >> 7, row = idx & (PT - 1);
+    Winv[idx] = (row >= kcol) ? S[kcol * PLD + row + 1] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Driver.  Outer panels of 4 tiles (512 columns): inside a panel every 128-wide
+// step factors its diagonal tile, solves the rows below against the explicit
+// inverse and updates the panel's remaining columns (K = 128); the matrix right
+// of the panel then gets one SYRK update with K = 512, which is where the
+// flops are.
+// ---------------------------------------------------------------------------
+int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmemBytes);
+    attr_done = true;
+  }
+  cudaMemsetAsync(ws.info, 0, sizeof(int), st);
+  const int64_t nt = n_pad / kTile;
+  const int64_t outer = 4;
+  for (int64_t J0 = 0; J0 < nt; J0 += outer) {
+    const int64_t jb = std::min<int64_t>(outer, nt - J0);
+    for (int64_t jj = J0; jj < J0 + jb; ++jj) {
+      double* Ajj = A + jj * kTile * ld + jj * kTile;
+      double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;
+      note_launch();
+      potrf_tile_kernel<<<1, 256, kPotrfSmemBytes, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
+      const int64_t below = n_pad - (jj + 1) * kTile;
+      if (below <= 0) continue;
+      double* panel = Ajj + kTile;  // rows below the diagonal tile, 128 columns
+      // X = A * W^T  (in place: a CTA reads all of its 128 x 128 block before writing it)
+      launch_gemm_nt(1, below, kTile, kTile, panel, ld, Wjj, kTile, panel, ld, 0, st);
+      const int64_t rest = (J0 + jb - jj - 1) * kTile;  // remaining columns of this outer panel
+      if (rest > 0)
+        launch_gemm_nt(0, below, rest, kTile, panel, ld, panel, ld, Ajj + kTile * ld + kTile, ld, 1, st);
+    }
+    const int64_t done = (J0 + jb) * kTile;
+    const int64_t trail = n_pad - done;
+    if (trail > 0) {
+      const double* P = A + J0 * kTile * ld + done;  // rows [done, n_pad), columns of the panel
+      launch_gemm_nt(0, trail, trail, jb * kTile, P, ld, P, ld, A + done * ld + done, ld, 1, st);
+    }
+  }
+  return 0;
+}
+
+}  // namespace cocons

@@ -1,0 +1,178 @@
+// Post-factorisation kernels (K6/K7): log-determinant, blocked forward
+// substitution with many right-hand sides, and the small Gram reductions from
+// which the ML / profile / REML quadratic forms are taken.  They replace
+//   sum(log(diag(cholS)))                          R/neg2loglikelihood.R:153,208,267
+//   forwardsolve(cholS, ., transpose=TRUE, ...)    :145-147, :214-217, :273-275
+//   crossprod(.)                                   :148, :157, :214, :276, :285
+// All of them are HBM-bound: the factor is streamed once per block of
+// right-hand sides (4 n^2 bytes).
+#include "../../include/cocons_b200.h"
+#include "common.cuh"
+
+namespace cocons {
+
+// sum_{i<n} log L_ii, one CTA, fixed summation order (deterministic)
+__global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, int64_t n, int64_t ld,
+                                                      double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s += log(L[i * ld + i]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+void launch_logdet(const double* L, int64_t n, int64_t ld, double* out, cudaStream_t st) {
+  note_launch();
+  logdet_kernel<<<1, 1024, 0, st>>>(L, n, ld, out);
+}
+
+// ---------------------------------------------------------------------------
+// One step J of the blocked forward substitution  L Y = B  (B overwritten by
+// partially updated right-hand sides, Y a separate buffer):
+//     y_J = inv(L_JJ) b_J ;   b_I -= L_IJ y_J  for every tile row I > J.
+// CTA 0 writes y_J; every CTA recomputes y_J in shared memory (a 128 x 128
+// product out of L2) instead of waiting for another CTA, then updates its own
+// 128 rows.  NR right-hand sides are carried in registers per pass.
+// ---------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, int64_t ld,
+                                                       const double* __restrict__ Winv, double* __restrict__ B,
+                                                       double* __restrict__ Y, int64_t ldb, int64_t J, int nr) {
+  __shared__ double bj[NR][kTile];
+  __shared__ double yj[NR][kTile];
+  __shared__ double part[NR][256];
+  const int tid = threadIdx.x;
+  const int64_t j0 = J * kTile;
+  for (int idx = tid; idx < NR * kTile; idx += 256) {
+    const int c = idx / kTile, k = idx % kTile;
+    bj[c][k] = (c < nr) ? B[(int64_t)c * ldb + j0 + k] : 0.0;
+  }
+  __syncthreads();
+  // y = W b: thread (row = tid & 127, half = tid >> 7) sums half of the k range
+  {
+    const int row = tid & (kTile - 1), h = tid >> 7;
+    double acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+    const int kbeg = h ? (row + 2) / 2 : 0, kend = h ? row + 1 : (row + 2) / 2;
+    for (int k = kbeg; k < kend; ++k) {
+      const double w = Winv[(int64_t)k * kTile + row];
+#pragma unroll
+      for (int c = 0; c < NR; ++c) acc[c] = fma(w, bj[c][k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
+  }
+  __syncthreads();
+  if (tid < kTile) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const double y = part[c][tid] + part[c][tid + kTile];
+      yj[c][tid] = y;
+      if (blockIdx.x == 0 && c < nr) Y[(int64_t)c * ldb + j0 + tid] = y;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) return;
+  // rows of tile I = J + blockIdx.x: b_I -= L_IJ y_J
+  const int64_t i0 = (J + blockIdx.x) * kTile;
+  {
+    const int row = tid & (kTile - 1), h = tid >> 7;
+    double acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+    const double* Lp = L + (j0 + (int64_t)h * (kTile / 2)) * ld + i0 + row;
+#pragma unroll 4
+    for (int k = 0; k < kTile / 2; ++k) {
+      const double l = Lp[(int64_t)k * ld];
+#pragma unroll
+      for (int c = 0; c < NR; ++c) acc[c] = fma(l, yj[c][h * (kTile / 2) + k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
+  }
+  __syncthreads();
+  if (tid < kTile) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c)
+      if (c < nr) B[(int64_t)c * ldb + i0 + tid] -= part[c][tid] + part[c][tid + kTile];
+  }
+}
+
+// L (n_pad x n_pad, lower) Y = B for nrhs columns; on return B holds Y.
+// Y scratch is provided by the caller through the upper half of B's allocation:
+// B must have room for 2*nrhs columns of ldb doubles.
+void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* winv, double* B, int64_t ldb, int nrhs,
+                   cudaStream_t st) {
+  const int64_t nt = n_pad / kTile;
+  double* Y = B + (int64_t)nrhs * ldb;
+  for (int c0 = 0; c0 < nrhs; c0 += 8) {
+    const int nr = (nrhs - c0 < 8) ? nrhs - c0 : 8;
+    double* Bc = B + (int64_t)c0 * ldb;
+    double* Yc = Y + (int64_t)c0 * ldb;
+    for (int64_t J = 0; J < nt; ++J) {
+      const unsigned blocks = (unsigned)(nt - J);
+      const double* W = winv + J * (int64_t)kTile * kTile;
+      note_launch();
+      if (nr == 1)
+        fwd_step_kernel<1><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
+      else if (nr == 2)
+        fwd_step_kernel<2><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
+      else if (nr <= 4)
+        fwd_step_kernel<4><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
+      else
+        fwd_step_kernel<8><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
+    }
+  }
+  cudaMemcpyAsync(B, Y, sizeof(double) * (size_t)nrhs * (size_t)ldb, cudaMemcpyDeviceToDevice, st);
+}
+
+// ---------------------------------------------------------------------------
+// G = Y^T Y for a tall n x k block (k <= 16), two deterministic passes.
+// ---------------------------------------------------------------------------
+constexpr int kGramMaxK = 16;
+constexpr int kGramBlocks = 296;
+
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ldy, int k,
+                                                           double* __restrict__ partial) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  for (int a = 0; a < k; ++a)
+    for (int b = 0; b <= a; ++b) {
+      double s = 0.0;
+      for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n; i += (int64_t)gridDim.x * 256)
+        s = fma(Y[(int64_t)a * ldy + i], Y[(int64_t)b * ldy + i], s);
+      red[tid] = s;
+      __syncthreads();
+      for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) red[tid] += red[tid + w];
+        __syncthreads();
+      }
+      if (tid == 0) partial[(int64_t)blockIdx.x * kGramMaxK * kGramMaxK + a * kGramMaxK + b] = red[0];
+      __syncthreads();
+    }
+}
+
+__global__ void gram_final_kernel(const double* __restrict__ partial, int nblocks, int k, double* __restrict__ G) {
+  const int a = threadIdx.x / kGramMaxK, b = threadIdx.x % kGramMaxK;
+  if (a >= k || b > a) return;
+  double s = 0.0;
+  for (int blk = 0; blk < nblocks; ++blk) s += partial[(int64_t)blk * kGramMaxK * kGramMaxK + a * kGramMaxK + b];
+  G[a * k + b] = s;
+  G[b * k + a] = s;
+}
+
+// G (k x k, host layout row-major == column-major by symmetry); scratch: kGramBlocks*256 doubles after G
+void launch_gram(const double* Y, int64_t n, int64_t ldy, int k, double* G, cudaStream_t st) {
+  double* partial = G + kGramMaxK * kGramMaxK;
+  note_launch(2);
+  gram_partial_kernel<<<kGramBlocks, 256, 0, st>>>(Y, n, ldy, k, partial);
+  gram_final_kernel<<<1, kGramMaxK * kGramMaxK, 0, st>>>(partial, kGramBlocks, k, G);
+}
+
+}  // namespace cocons

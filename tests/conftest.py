@@ -1,0 +1,77 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def datasets():
+    return dict(np.load(os.path.join(GOLD, "datasets.npz"), allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def cov_cases():
+    raw = np.load(os.path.join(GOLD, "cov_cases.npz"), allow_pickle=False)
+    cases = {}
+    for key in raw.files:
+        name, field = key.split("__")
+        cases.setdefault(name, {})[field] = raw[key]
+    return cases
+
+
+@pytest.fixture(scope="session")
+def n2ll_cases():
+    with open(os.path.join(GOLD, "n2ll_cases.json")) as f:
+        doc = json.load(f)
+    out = {}
+    for c in doc["cases"]:
+        c = dict(c)
+        c["par_pos"] = {k: (np.array(v, dtype=bool) if isinstance(v, list) else v) for k, v in c["par_pos"].items()}
+        c["theta"] = np.array(c["theta"])
+        out[c["name"]] = c
+    return out
+
+
+def theta_dict(theta6):
+    from oracle.cov import ASPECTS
+    return {k: np.array(theta6[i]) for i, k in enumerate(ASPECTS)}
+
+
+def relerr(a, b):
+    """max |a-b| / |b| over entries, with exact agreement required where b == 0."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    zero = b == 0
+    if np.any(zero) and not np.array_equal(a[zero], b[zero]):
+        return np.inf
+    if np.all(zero):
+        return 0.0
+    return float(np.max(np.abs(a[~zero] - b[~zero]) / np.abs(b[~zero])))
+
+
+def case_design(case, datasets):
+    """(locs, X_std, z, x_betas=X) of an n2ll golden case, rebuilt from the dataset fixture with the
+    PRODUCT's getScale (so the host mirror is exercised too)."""
+    from cocons_b200 import getScale
+    n = case["n"]
+    if case["dataset"] == "holes":
+        M = datasets["holes_training"]
+        cols, z = [2, 3], M[:n, 4]
+    elif case["dataset"] == "holes_bm":
+        M = datasets["holes_bm_training"]
+        cols, z = [2, 3], datasets["holes_bm_training_z"][:n]
+    else:
+        M = datasets["stripes_training"]
+        cols, z = [2, 3, 4], M[:n, 5]
+    X = getScale(np.column_stack([np.ones(n)] + [M[:n, c] for c in cols]))["std.covs"]
+    return M[:n, :2], X, np.asarray(z, dtype=np.float64).reshape(n, -1)

@@ -1,0 +1,137 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol the header
+declares, the host mirror of the R interface agrees with the oracle's literal restatement, the
+device math header agrees with mpmath when compiled for the host, and - without a GPU - every
+computing entry point fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+import cocons_b200 as cb
+from cocons_b200 import _lib
+from oracle import rmirror
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "cocons_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cocons_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    L = _lib.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "libcocons_b200.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "no ctypes signature for %s" % s
+    assert sorted(_lib.SIGNATURES) == syms
+    assert L.cocons_version() >= 100
+
+
+def test_library_is_sm100a_dmma_code():
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass
+    assert "DMMA.8x8x4" in sass  # FP64 tensor-core trailing update
+    assert "LDGSTS" in sass  # async global->shared operand feed
+
+
+def test_sumsmoothlone_matches_oracle():
+    from oracle import cov
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(12) * np.array([1, 1e-5, 1, 1e-6, 0, 1, 1, 1e-4, 1, 1e-3, 1e-7, 2])
+    assert cb.sumsmoothlone(x, 0.3) == cov.sumsmoothlone(x, 0.3)
+    assert cb.sumsmoothlone([], 0.3) == 0.0
+
+
+@pytest.mark.skipif(_lib.lib().cocons_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_a_device():
+    th = {k: np.zeros(1) for k in _lib.ASPECTS}
+    with pytest.raises(cb.CoconsError, match="no CPU fallback|no CUDA device"):
+        cb.cov_rns(th, np.zeros((3, 2)), np.ones((3, 1)), [0.5, 0.5])
+    with pytest.raises(cb.CoconsError):
+        cb.DenseLikelihood(np.zeros((3, 2)), np.ones((3, 1)), np.zeros(3))
+    with pytest.raises(cb.CoconsError):
+        cb.GetNeg2loglikelihood(np.zeros(2), {"mean": 0.0, "std.dev": np.array([True]), "scale": np.array([True]),
+                                              "aniso": 0.0, "tilt": 0.0, "smooth": 0.5, "nugget": -np.inf},
+                                np.zeros((3, 2)), np.ones((3, 1)), [0.5, 0.5], np.zeros(3), 3, (0, 0, 0))
+
+
+def test_model_lists_scale_and_penalty_match_the_literal_restatement():
+    rng = np.random.default_rng(5)
+    par_pos = {"mean": np.array([True, True, False, True]), "std.dev": np.array([True, False, True, True]),
+               "scale": np.array([True, True, True, False]), "aniso": np.array([True, False, False, False]),
+               "tilt": 0.0, "smooth": np.array([True, True, True, True]), "nugget": -np.inf}
+    k = sum(int(v.sum()) for v in par_pos.values() if isinstance(v, np.ndarray))
+    theta = rng.standard_normal(k)
+    for typ in ("diff", "classic"):
+        a, b = cb.getModelLists(theta, par_pos, typ), rmirror.get_model_lists(theta, par_pos, typ)
+        assert list(a) == list(b)
+        for key in a:
+            assert np.array_equal(a[key], b[key], equal_nan=True)
+    X = np.column_stack([np.ones(40), rng.standard_normal((40, 3)) * [1, 5, 0.1] + [0, 3, -2]])
+    a, b = cb.getScale(X), rmirror.get_scale(X)
+    for key in a:
+        assert np.array_equal(a[key], b[key])
+    a2 = cb.getScale(X[:7], a["mean.vector"], a["sd.vector"])["std.covs"]
+    assert np.array_equal(a2, rmirror.get_scale(X[:7], b["mean.vector"], b["sd.vector"])["std.covs"])
+    tl = cb.getModelLists(theta, par_pos, "diff")
+    tl["nugget"][0] = -2.0
+    from cocons_b200.api import _getPen
+    for lam in ((0, 0, 0), (0.1, 0.02, 0.5)):
+        assert _getPen(40, lam, tl, [0.5, 2.5]) == rmirror.get_pen(40, lam, tl, [0.5, 2.5])
+
+
+def test_design_matrix_mirror(datasets):
+    H = datasets["holes_training"][:30]
+    data = {"x": H[:, 0], "y": H[:, 1], "cov_x": H[:, 2], "cov_y": H[:, 3], "z": H[:, 4]}
+    ml = {"mean": "~ 1 + cov_x", "std.dev": "~ 1 + cov_x + cov_y", "scale": "~ 1 + cov_y", "aniso": 0, "tilt": 0,
+          "smooth": 1.5, "nugget": -np.inf}
+    dm = cb.getDesignMatrix(ml, data)
+    assert dm["colnames"] == ["(Intercept)", "cov_x", "cov_y"]
+    assert np.array_equal(dm["model.matrix"][:, 1], H[:, 2])
+    assert dm["par.pos"]["mean"].tolist() == [True, True, False]
+    assert dm["par.pos"]["scale"].tolist() == [True, False, True]
+    assert dm["par.pos"]["smooth"] == 1.5 and np.isneginf(dm["par.pos"]["nugget"])
+    obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml)
+    assert list(obj.model_list) == list(cb.api.DICTIONARY)
+    assert obj.info["smooth.limits"].tolist() == [1.5, 1.5]  # R/cocons.R:157-162
+    assert obj.z.shape == (30, 1)
+    with pytest.raises(ValueError):
+        cb.coco("foo", data, H[:, :2], H[:, 4], ml)  # tests/coco_test.R:260-267
+
+
+def test_device_bessel_header_on_host_against_mpmath(tmp_path):
+    """bessel.cuh also compiles as plain C++: check the exact code the kernel inlines."""
+    src = tmp_path / "bh.cpp"
+    src.write_text('#include "bessel.cuh"\n'
+                   'extern "C" double h_k(double nu, double x){ return cocons::bessel_k(nu, x); }\n'
+                   'extern "C" double h_m(double nu, double x){ return cocons::matern_corr(nu, x); }\n')
+    so = tmp_path / "libbh.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-I" + os.path.join(ROOT, "cocons_b200", "csrc"), str(src), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    for f in (lib.h_k, lib.h_m):
+        f.argtypes, f.restype = [ctypes.c_double] * 2, ctypes.c_double
+    mp.mp.dps = 40
+    rng = np.random.default_rng(1)
+    nus = [0.05, 0.3, 0.5, 1.0, 1.5, 1.9, 2.5, 3.0, 3.7, 5.2] + list(rng.uniform(0.02, 3.5, 10))
+    xs = [1e-12, 1e-6, 0.1, 1.0, 2.0, 2.0000001, 5, 16.5, 24.9, 25, 25.1, 50, 300, 705.9] + list(
+        np.exp(rng.uniform(np.log(1e-6), np.log(705), 40)))
+    worst_k = worst_m = 0.0
+    for nu in nus:
+        for x in xs:
+            ref = mp.besselk(mp.mpf(nu), mp.mpf(x))
+            worst_k = max(worst_k, float(abs((mp.mpf(lib.h_k(nu, x)) - ref) / ref)))
+            refm = mp.mpf(2) ** (1 - mp.mpf(nu)) / mp.gamma(mp.mpf(nu)) * mp.mpf(x) ** mp.mpf(nu) * ref
+            worst_m = max(worst_m, float(abs((mp.mpf(lib.h_m(nu, x)) - refm) / refm)))
+    assert worst_k < 1e-14, worst_k
+    assert worst_m < 3e-14, worst_m
