@@ -196,7 +196,7 @@ struct cocons_ctx {
   double* dSite = nullptr;
   int* dOrig = nullptr;
   double* dA = nullptr;
-  CholWorkspace ws{nullptr, nullptr};
+  CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr};
   double* dRhs = nullptr;   // n_pad x 2*kMaxRhs
   double* dGram = nullptr;  // Gram + partials + scalars
   // pinned staging
@@ -371,7 +371,8 @@ void cocons_ctx_destroy(cocons_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->dX), cudaFree(c->dLocs), cudaFree(c->dZ), cudaFree(c->dXb), cudaFree(c->dTheta), cudaFree(c->dSite);
-  cudaFree(c->dOrig), cudaFree(c->dA), cudaFree(c->ws.winv), cudaFree(c->ws.info), cudaFree(c->dRhs);
+  cudaFree(c->dOrig), cudaFree(c->dA), cudaFree(c->dRhs);
+  chol_workspace_destroy(&c->ws);
   cudaFree(c->dGram);
   if (c->hStage) cudaFreeHost(c->hStage);
   if (c->hInfo) cudaFreeHost(c->hInfo);
@@ -421,8 +422,11 @@ int cocons_ctx_create(int device, int64_t n, int64_t p, int64_t r, const double*
   CTX_TRY(cudaMalloc(&c->dSite, sizeof(double) * SF_COUNT * np));
   CTX_TRY(cudaMalloc(&c->dOrig, sizeof(int) * np));
   CTX_TRY(cudaMalloc(&c->dA, sizeof(double) * np * np));
-  CTX_TRY(cudaMalloc(&c->ws.winv, sizeof(double) * (np / kTile) * kTile * kTile));
-  CTX_TRY(cudaMalloc(&c->ws.info, sizeof(int)));
+  if (chol_workspace_create(np, &c->ws) != 0) {
+    set_error("ctx_create: out of device memory for the factorisation workspace");
+    cocons_ctx_destroy(c);
+    return COCONS_ERR_ALLOC;
+  }
   CTX_TRY(cudaMalloc(&c->dRhs, sizeof(double) * np * 2 * kMaxRhs));
   CTX_TRY(cudaMalloc(&c->dGram, sizeof(double) * (kMaxRhs * kMaxRhs * 300 + 16)));
   CTX_TRY(cudaMallocHost(&c->hStage, sizeof(double) * (7 * p + kMaxRhs * kMaxRhs + 16)));
@@ -844,16 +848,15 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
   if (rc) return rc;
   PredBlock blk;
   double *dS = nullptr, *dE = nullptr, *dO = nullptr;
-  CholWorkspace ws2{nullptr, nullptr};
-  auto cleanup = [&]() { cudaFree(dS), cudaFree(dE), cudaFree(dO), cudaFree(ws2.winv), cudaFree(ws2.info); };
+  CholWorkspace ws2{nullptr, nullptr, nullptr, nullptr, nullptr};
+  auto cleanup = [&]() { cudaFree(dS), cudaFree(dE), cudaFree(dO), chol_workspace_destroy(&ws2); };
   if (cudaMalloc(&blk.dXp, sizeof(double) * mp * p) != cudaSuccess ||
       cudaMalloc(&blk.dLp, sizeof(double) * mp * 2) != cudaSuccess ||
       cudaMalloc(&blk.dSp, sizeof(double) * SF_COUNT * mp) != cudaSuccess ||
       cudaMalloc(&blk.dC, sizeof(double) * mp * np) != cudaSuccess ||
       cudaMalloc(&dS, sizeof(double) * mp * mp) != cudaSuccess || cudaMalloc(&dE, sizeof(double) * mp * k) != cudaSuccess ||
       cudaMalloc(&dO, sizeof(double) * mp * k) != cudaSuccess ||
-      cudaMalloc(&ws2.winv, sizeof(double) * (mp / kTile) * kTile * kTile) != cudaSuccess ||
-      cudaMalloc(&ws2.info, sizeof(int)) != cudaSuccess) {
+      chol_workspace_create(mp, &ws2) != 0) {
     cleanup();
     set_error("sim_cond: out of device memory");
     return COCONS_ERR_ALLOC;

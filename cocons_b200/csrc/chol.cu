@@ -29,9 +29,20 @@ namespace cocons {
 // consecutive rows (32 B) and a quad 128 contiguous bytes of a column.  The
 // same binding makes every operand fetch one conflict-free LDS.128.
 // ---------------------------------------------------------------------------
-constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 4;
-constexpr int GLDS = 132;  // padded leading dimension of a shared k-row (== 4 mod 16)
-constexpr int kGemmSmemBytes = GSTAGES * 2 * GBK * GLDS * (int)sizeof(double);
+constexpr int GBM = 128, GBK = 16, GSTAGES = 4;
+constexpr int GLDA = GBM + 4;  // padded leading dimension of a shared k-row (== 4 mod 16: conflict-free LDS.128)
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kWarpsJ = BN / 32;            // warp tile is 64(i) x 32(j)
+  static constexpr int kThreads = 2 * kWarpsJ * 32;  // 2 warps along i
+  static constexpr int kLdb = BN + 4;
+  static constexpr int kStageDoubles = GBK * (GLDA + kLdb);
+  static constexpr int kSmemBytes = GSTAGES * kStageDoubles * (int)sizeof(double);
+  // BN = 64: 128 threads x 192 registers and ~100 KB of shared memory, so TWO CTAs share an SM and
+  // one runs its main loop while the other is in its prologue / read-modify-write epilogue
+  static constexpr int kMinBlocks = (BN == 64) ? 2 : 1;
+};
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -49,26 +60,34 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// tile index -> (bi, bj) of a lower trapezoid with ni >= nj tile rows/cols, column by column
+// Tile index -> (bi, bj) of the lower trapezoid of a matrix whose origin lies on the diagonal:
+// ni tile rows of 128, column tiles of BN = 128 / W (W = 1 or 2); tile (bi, bj) is needed when its
+// last row reaches its first column, i.e. bi >= bj / W.  Tiles are numbered column by column.
+template <int W>
 __device__ __forceinline__ void trapezoid_decode(int64_t t, int ni, int& bi, int& bj) {
-  // tiles before column c: S(c) = c*ni - c(c-1)/2
+  // groups of W columns share the diagonal block c; tiles before group c: W * (c*ni - c(c-1)/2)
+  const int64_t tw = t / W;
   const double b = (double)ni + 0.5;
-  int c = (int)(b - sqrt(b * b - 2.0 * (double)t));
+  int c = (int)(b - sqrt(b * b - 2.0 * (double)tw));
   if (c < 0) c = 0;
-  while ((int64_t)(c + 1) * ni - (int64_t)(c + 1) * c / 2 <= t) ++c;
-  while ((int64_t)c * ni - (int64_t)c * (c - 1) / 2 > t) --c;
-  bj = c;
-  bi = c + (int)(t - ((int64_t)c * ni - (int64_t)c * (c - 1) / 2));
+  auto before = [&](int cc) { return (int64_t)W * ((int64_t)cc * ni - (int64_t)cc * (cc - 1) / 2); };
+  while (before(c + 1) <= t) ++c;
+  while (before(c) > t) --c;
+  const int64_t rem = t - before(c);
+  const int per = ni - c;
+  bj = c * W + (int)(rem / per);
+  bi = c + (int)(rem % per);
 }
 
-template <int ASSIGN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int ASSIGN>
+__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, GemmCfg<BN>::kMinBlocks)
     gemm_nt_kernel(int ni, int nj, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                    int64_t ldc, int lower_only) {
+  using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(16) double smem[];
   int bi, bj;
   if (lower_only) {
-    trapezoid_decode(blockIdx.x, ni, bi, bj);
+    trapezoid_decode<GBM / BN>(blockIdx.x, ni, bi, bj);
   } else {
     bj = blockIdx.x / ni;
     bi = blockIdx.x - bj * ni;
@@ -78,19 +97,23 @@ __global__ void __launch_bounds__(256, 1)
   const int g = lane >> 2, c4 = lane & 3;
   const int iw = (warp & 1) * 64, jw = (warp >> 1) * 32;
   const double* Ag = A + (int64_t)bi * GBM;
-  const double* Bg = B + (int64_t)bj * GBN;
+  const double* Bg = B + (int64_t)bj * BN;
 
-  auto As = [&](int s) { return smem + (size_t)s * (2 * GBK * GLDS); };
-  auto Bs = [&](int s) { return smem + (size_t)s * (2 * GBK * GLDS) + GBK * GLDS; };
+  auto As = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles; };
+  auto Bs = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles + GBK * GLDA; };
 
   auto load_stage = [&](int s, int64_t kb) {
     double* as = As(s);
     double* bs = Bs(s);
 #pragma unroll
-    for (int c = tid; c < GBK * (GBM / 2); c += 256) {
-      const int k = c >> 6, i2 = c & 63;
-      cp_async16(as + k * GLDS + 2 * i2, Ag + (kb * GBK + k) * lda + 2 * i2);
-      cp_async16(bs + k * GLDS + 2 * i2, Bg + (kb * GBK + k) * ldb + 2 * i2);
+    for (int c = tid; c < GBK * (GBM / 2); c += Cfg::kThreads) {
+      const int k = c / (GBM / 2), i2 = c % (GBM / 2);
+      cp_async16(as + k * GLDA + 2 * i2, Ag + (kb * GBK + k) * lda + 2 * i2);
+    }
+#pragma unroll
+    for (int c = tid; c < GBK * (BN / 2); c += Cfg::kThreads) {
+      const int k = c / (BN / 2), j2 = c % (BN / 2);
+      cp_async16(bs + k * Cfg::kLdb + 2 * j2, Bg + (kb * GBK + k) * ldb + 2 * j2);
     }
   };
 
@@ -122,13 +145,13 @@ __global__ void __launch_bounds__(256, 1)
       double fi[8], fj[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const double2 v = *reinterpret_cast<const double2*>(as + k * GLDS + 16 * u);
+        const double2 v = *reinterpret_cast<const double2*>(as + k * GLDA + 16 * u);
         fi[2 * u] = v.x;
         fi[2 * u + 1] = v.y;
       }
 #pragma unroll
       for (int v2 = 0; v2 < 2; ++v2) {
-        const double2 v = *reinterpret_cast<const double2*>(bs + k * GLDS + 16 * v2);
+        const double2 v = *reinterpret_cast<const double2*>(bs + k * Cfg::kLdb + 16 * v2);
         fj[2 * v2] = v.x;
         fj[2 * v2 + 1] = v.y;
       }
@@ -141,7 +164,7 @@ __global__ void __launch_bounds__(256, 1)
   cp_async_wait<0>();
 
   // epilogue: a thread owns rows r0..r0+3 of column j for every (a, u)
-  double* Cg = C + (int64_t)bj * GBN * ldc + (int64_t)bi * GBM;
+  double* Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int j = jw + 16 * (a >> 1) + 2 * g + (a & 1);
@@ -169,22 +192,34 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
+// mode 0: C -= A B^T on 128 x 64 tiles (two CTAs per SM); mode 1: C = A B^T on 128 x 128 tiles -
+// the in-place panel solve needs one CTA to own the whole 128-column block it overwrites.
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    attr_done = true;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaFuncSetAttribute(gemm_nt_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<128>::kSmemBytes);
+    attr_done[dev] = true;
   }
-  const int ni = (int)(M / GBM), nj = (int)(N / GBN);
-  int64_t tiles = lower_only ? ((int64_t)nj * ni - (int64_t)nj * (nj - 1) / 2) : (int64_t)ni * nj;
+  const int ni = (int)(M / GBM);
   note_launch();
-  if (mode == 1)
-    gemm_nt_kernel<1><<<(unsigned)tiles, 256, kGemmSmemBytes, st>>>(ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
-  else
-    gemm_nt_kernel<0><<<(unsigned)tiles, 256, kGemmSmemBytes, st>>>(ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+  if (mode == 1) {
+    const int nj = (int)(N / 128);
+    const int64_t tiles = lower_only ? ((int64_t)nj * ni - (int64_t)nj * (nj - 1) / 2) : (int64_t)ni * nj;
+    gemm_nt_kernel<128, 1><<<(unsigned)tiles, GemmCfg<128>::kThreads, GemmCfg<128>::kSmemBytes, st>>>(
+        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+  } else {
+    const int nj = (int)(N / 64);
+    const int ng = (int)(N / 128);  // column groups sharing a diagonal block
+    const int64_t tiles = lower_only ? 2 * ((int64_t)ng * ni - (int64_t)ng * (ng - 1) / 2) : (int64_t)ni * nj;
+    gemm_nt_kernel<64, 0><<<(unsigned)tiles, GemmCfg<64>::kThreads, GemmCfg<64>::kSmemBytes, st>>>(
+        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -275,37 +310,81 @@ __global__ void __launch_bounds__(256, 1)
 // of the panel then gets one SYRK update with K = 512, which is where the
 // flops are.
 // ---------------------------------------------------------------------------
+int chol_workspace_create(int64_t n_pad, CholWorkspace* ws) {
+  ws->winv = nullptr, ws->info = nullptr, ws->panel_stream = nullptr, ws->ev_a = nullptr, ws->ev_p = nullptr;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority (numerically lowest)
+  if (cudaMalloc(&ws->winv, sizeof(double) * (n_pad / kTile) * kTile * kTile) != cudaSuccess ||
+      cudaMalloc(&ws->info, sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ws->panel_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ws->ev_p, cudaEventDisableTiming) != cudaSuccess) {
+    chol_workspace_destroy(ws);
+    return COCONS_ERR_ALLOC;
+  }
+  return 0;
+}
+
+void chol_workspace_destroy(CholWorkspace* ws) {
+  cudaFree(ws->winv), cudaFree(ws->info);
+  if (ws->panel_stream) cudaStreamDestroy(ws->panel_stream);
+  if (ws->ev_a) cudaEventDestroy(ws->ev_a);
+  if (ws->ev_p) cudaEventDestroy(ws->ev_p);
+  ws->winv = nullptr, ws->info = nullptr, ws->panel_stream = nullptr, ws->ev_a = nullptr, ws->ev_p = nullptr;
+}
+
+// one outer panel: tiles [J0, J0+jb), every 128-wide step on stream `st`
+static void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws, int64_t J0, int64_t jb,
+                         cudaStream_t st) {
+  for (int64_t jj = J0; jj < J0 + jb; ++jj) {
+    double* Ajj = A + jj * kTile * ld + jj * kTile;
+    double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;
+    note_launch();
+    potrf_tile_kernel<<<1, 256, kPotrfSmemBytes, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
+    const int64_t below = n_pad - (jj + 1) * kTile;
+    if (below <= 0) continue;
+    double* panel = Ajj + kTile;  // rows below the diagonal tile, 128 columns
+    // X = A * W^T  (in place: a CTA reads all of its 128 x 128 block before writing it)
+    launch_gemm_nt(1, below, kTile, kTile, panel, ld, Wjj, kTile, panel, ld, 0, st);
+    const int64_t rest = (J0 + jb - jj - 1) * kTile;  // remaining columns of this outer panel
+    if (rest > 0) launch_gemm_nt(0, below, rest, kTile, panel, ld, panel, ld, Ajj + kTile * ld + kTile, ld, 1, st);
+  }
+}
+
+// Look-ahead: the update by panel J is split into (a) the columns of panel J+1 and (b) everything
+// to their right.  As soon as (a) is done, panel J+1 is factored on a high-priority side stream
+// while (b) - where the flops are - keeps the SMs busy on the main stream.
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
     cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmemBytes);
-    attr_done = true;
+    attr_done[dev] = true;
   }
   cudaMemsetAsync(ws.info, 0, sizeof(int), st);
   const int64_t nt = n_pad / kTile;
   const int64_t outer = 4;
+  factor_panel(A, n_pad, ld, ws, 0, std::min<int64_t>(outer, nt), st);
   for (int64_t J0 = 0; J0 < nt; J0 += outer) {
     const int64_t jb = std::min<int64_t>(outer, nt - J0);
-    for (int64_t jj = J0; jj < J0 + jb; ++jj) {
-      double* Ajj = A + jj * kTile * ld + jj * kTile;
-      double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;
-      note_launch();
-      potrf_tile_kernel<<<1, 256, kPotrfSmemBytes, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
-      const int64_t below = n_pad - (jj + 1) * kTile;
-      if (below <= 0) continue;
-      double* panel = Ajj + kTile;  // rows below the diagonal tile, 128 columns
-      // X = A * W^T  (in place: a CTA reads all of its 128 x 128 block before writing it)
-      launch_gemm_nt(1, below, kTile, kTile, panel, ld, Wjj, kTile, panel, ld, 0, st);
-      const int64_t rest = (J0 + jb - jj - 1) * kTile;  // remaining columns of this outer panel
-      if (rest > 0)
-        launch_gemm_nt(0, below, rest, kTile, panel, ld, panel, ld, Ajj + kTile * ld + kTile, ld, 1, st);
-    }
     const int64_t done = (J0 + jb) * kTile;
     const int64_t trail = n_pad - done;
-    if (trail > 0) {
-      const double* P = A + J0 * kTile * ld + done;  // rows [done, n_pad), columns of the panel
-      launch_gemm_nt(0, trail, trail, jb * kTile, P, ld, P, ld, A + done * ld + done, ld, 1, st);
+    if (trail <= 0) break;
+    const int64_t nb_next = std::min<int64_t>(outer, nt - (J0 + jb));
+    const int64_t wnext = nb_next * kTile;
+    const double* P = A + J0 * kTile * ld + done;  // rows [done, n_pad) of panel J
+    launch_gemm_nt(0, trail, wnext, jb * kTile, P, ld, P, ld, A + done * ld + done, ld, 1, st);  // (a)
+    cudaEventRecord(ws.ev_a, st);
+    cudaStreamWaitEvent(ws.panel_stream, ws.ev_a, 0);
+    factor_panel(A, n_pad, ld, ws, J0 + jb, nb_next, ws.panel_stream);
+    cudaEventRecord(ws.ev_p, ws.panel_stream);
+    const int64_t rest = trail - wnext;
+    if (rest > 0) {  // (b)
+      const double* P2 = P + wnext;
+      launch_gemm_nt(0, rest, rest, jb * kTile, P2, ld, P2, ld, A + (done + wnext) * ld + done + wnext, ld, 1, st);
     }
+    cudaStreamWaitEvent(st, ws.ev_p, 0);
   }
   return 0;
 }

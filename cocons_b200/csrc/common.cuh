@@ -74,9 +74,13 @@ void morton_order(int64_t n, const double* locs, int64_t* perm);
 
 // ---- chol.cu -------------------------------------------------------------
 struct CholWorkspace {
-  double* winv;  // (n_pad/kTile) inverted diagonal tiles, kTile x kTile each
-  int* info;     // device flag: 0 ok, k > 0 first non-positive pivot (1-based)
+  double* winv;               // (n_pad/kTile) inverted diagonal tiles, kTile x kTile each
+  int* info;                  // device flag: 0 ok, k > 0 first non-positive pivot (1-based)
+  cudaStream_t panel_stream;  // high-priority side stream for the look-ahead panel
+  cudaEvent_t ev_a, ev_p;
 };
+int chol_workspace_create(int64_t n_pad, CholWorkspace* ws);
+void chol_workspace_destroy(CholWorkspace* ws);
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st);
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st);
