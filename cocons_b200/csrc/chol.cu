@@ -223,93 +223,136 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
 }
 
 // ---------------------------------------------------------------------------
-// Diagonal tile: unblocked Cholesky of a 128 x 128 tile held in shared memory,
-// followed by the explicit inverse W = L^-1 (lower triangular), which turns the
-// panel solve and the later forward substitutions into plain products.
-// Shared layout: L(i,j), j <= i, at S[i][j]; W(r,c), c <= r, at S[c][r+1]
-// (the otherwise unused strict upper part), row stride 129 doubles.
+// Diagonal tile: Cholesky of a 128 x 128 tile and its explicit inverse W = L^-1
+// (which turns the panel solve and the later forward substitutions into plain
+// products), with the whole tile held in REGISTERS.
+//
+// 256 threads as a 16 x 16 grid, thread (tx, ty) = (tid >> 4, tid & 15) owns the
+// 2-D cyclic set (i = ty + 16 a, j = tx + 16 b), a >= b.  The 16 threads that
+// share a column index form a half-warp, so the pivot is broadcast by shuffle;
+// the scaled column travels through a double-buffered 1 KB shared vector and
+// every thread applies the rank-1 update to its own registers: one block
+// barrier per column, no shared-memory matrix.  The inverse is built row by
+// row the same way (row of L through shared memory, partial dot products per
+// thread, half-warp shuffle reduction).
 // ---------------------------------------------------------------------------
 constexpr int PT = kTile;
-constexpr int PLD = PT + 1;
-constexpr int kPotrfSmemBytes = PT * PLD * (int)sizeof(double);
 
 __global__ void __launch_bounds__(256, 1)
     potrf_tile_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int* __restrict__ info,
                       int first_index) {
-  extern __shared__ __align__(16) double S[];
-  __shared__ double red[256];
+  __shared__ double colbuf[2][PT];
+  __shared__ double rowbuf[2][PT];
   __shared__ int fail;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tx = tid >> 4, ty = tid & 15;
+  const unsigned hmask = 0xFFFFu << (lane & 16);
+  double r[8][8], w[8][8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      w[a][b] = 0.0;
+      r[a][b] = (a >= b) ? A[(int64_t)(tx + 16 * b) * ld + ty + 16 * a] : 0.0;
+    }
   if (tid == 0) fail = 0;
-  // load the lower triangle (column-major global, coalesced along i)
-  for (int idx = tid; idx < PT * PT; idx += 256) {
-    const int j = idx >> 7, i = idx & (PT - 1);
-    if (i >= j) S[i * PLD + j] = A[(int64_t)j * ld + i];
-  }
   __syncthreads();
-  for (int k = 0; k < PT; ++k) {
-    const double d = S[k * PLD + k];
-    if (!(d > 0.0)) {  // non-positive or NaN pivot: dpotrf's info = k+1
-      if (tid == 0) {
-        fail = 1;
-        atomicCAS(info, 0, first_index + k + 1);
+
+  bool stop = false;
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    for (int kx = 0; kx < 16 && !stop; ++kx) {
+      const int k = kb * 16 + kx;
+      double* cb = colbuf[k & 1];
+      if (tx == kx) {  // the half-warp that owns column k
+        const double d = __shfl_sync(hmask, r[kb][kb], (lane & 16) | kx);
+        const double piv = sqrt(d), rinv = 1.0 / piv;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int i = ty + 16 * a;
+          if (a >= kb) {
+            double v = r[a][kb];
+            v = (i > k) ? v * rinv : ((i == k) ? piv : v);
+            r[a][kb] = v;
+            cb[i] = (i > k) ? v : 0.0;
+          } else {
+            cb[i] = 0.0;
+          }
+        }
+        if (!(d > 0.0) && ty == kx) {  // non-positive or NaN pivot: dpotrf's info = k+1
+          fail = 1;
+          atomicCAS(info, 0, first_index + k + 1);
+        }
       }
-      break;
+      __syncthreads();
+      stop = (fail != 0);
+      if (!stop) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b >= kb) {
+            const double lj = cb[tx + 16 * b];  // zero for j <= k: finished columns stay untouched
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              if (a >= b) r[a][b] = fma(-cb[ty + 16 * a], lj, r[a][b]);
+          }
+        }
+      }
     }
-    const double piv = sqrt(d);
-    __syncthreads();  // everyone has read the pivot
-    if (tid == 0) S[k * PLD + k] = piv;
-    for (int i = k + 1 + tid; i < PT; i += 256) S[i * PLD + k] = S[i * PLD + k] / piv;
-    __syncthreads();
-    // trailing update: warp per column j, lanes over rows i >= j
-    for (int j = k + 1 + warp; j < PT; j += 8) {
-      const double ljk = S[j * PLD + k];
-      for (int i = j + lane; i < PT; i += 32) S[i * PLD + j] = fma(-S[i * PLD + k], ljk, S[i * PLD + j]);
+  }
+  if (stop) return;
+
+  // L back to the matrix; the strict upper part of the tile is zeroed
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int i = ty + 16 * a, j = tx + 16 * b;
+      A[(int64_t)j * ld + i] = (a >= b && i >= j) ? r[a][b] : 0.0;
     }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (fail) return;
-  // write L back (lower part; the strict upper part of the tile is zeroed)
-  for (int idx = tid; idx < PT * PT; idx += 256) {
-    const int j = idx >> 7, i = idx & (PT - 1);
-    A[(int64_t)j * ld + i] = (i >= j) ? S[i * PLD + j] : 0.0;
-  }
+
   // W = L^-1 by rows: W[r][c] = (delta_rc - sum_{k=c}^{r-1} L[r][k] W[k][c]) / L[r][r]
-  // thread (c, h): column c = tid & 127, half h = tid >> 7 of the k range
-  const int c = tid & (PT - 1), h = tid >> 7;
-  for (int r = 0; r < PT; ++r) {
-    double part = 0.0;
-    if (c < r) {
-      const int len = r - c;
-      const int kbeg = c + (h ? (len + 1) / 2 : 0);
-      const int kend = h ? r : c + (len + 1) / 2;
-      for (int k = kbeg; k < kend; ++k) part = fma(S[r * PLD + k], S[c * PLD + k + 1], part);
+#pragma unroll
+  for (int rb = 0; rb < 8; ++rb) {
+    for (int rx = 0; rx < 16; ++rx) {
+      const int row = rb * 16 + rx;
+      double* rbuf = rowbuf[row & 1];
+      if (ty == rx) {  // the 16 threads holding row `row` of L publish it (zero right of the diagonal)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int j = tx + 16 * b;
+          rbuf[j] = (b <= rb && j <= row) ? r[rb][b] : 0.0;
+        }
+      }
+      __syncthreads();
+      const double dinv = 1.0 / rbuf[row];
+      double lk[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) lk[a] = (a <= rb && ty + 16 * a < row) ? rbuf[ty + 16 * a] : 0.0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b <= rb) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+            if (a >= b && a <= rb) s = fma(lk[a], w[a][b], s);
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(hmask, s, off);
+          const int c = tx + 16 * b;
+          if (ty == rx && c <= row) w[rb][b] = (((c == row) ? 1.0 : 0.0) - s) * dinv;
+        }
+      }
     }
-    red[tid] = part;
-    __syncthreads();
-    if (h == 0 && c <= r) {
-      const double s = red[c] + red[c + PT];
-      const double rhs = (c == r) ? 1.0 : 0.0;
-      S[c * PLD + r + 1] = (rhs - s) / S[r * PLD + r];
+  }
+  // Winv: 128 x 128 column-major, element (row, col) = W[row][col], zero above the diagonal
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int i = ty + 16 * a, j = tx + 16 * b;
+      Winv[j * PT + i] = (a >= b && i >= j) ? w[a][b] : 0.0;
     }
-    __syncthreads();
-  }
-  // Winv: 128 x 128 column-major, element (row c_, col k_) = W[c_][k_], zero above the diagonal
-  for (int idx = tid; idx < PT * PT; idx += 256) {
-    const int kcol = idx >> 7, row = idx & (PT - 1);
-    Winv[idx] = (row >= kcol) ? S[kcol * PLD + row + 1] : 0.0;
-  }
 }
 
-// ---------------------------------------------------------------------------
-// Driver.  Outer panels of 4 tiles (512 columns): inside a panel every 128-wide
-// step factors its diagonal tile, solves the rows below against the explicit
-// inverse and updates the panel's remaining columns (K = 128); the matrix right
-// of the panel then gets one SYRK update with K = 512, which is where the
-// flops are.
-// ---------------------------------------------------------------------------
 int chol_workspace_create(int64_t n_pad, CholWorkspace* ws) {
   ws->winv = nullptr, ws->info = nullptr, ws->panel_stream = nullptr, ws->ev_a = nullptr, ws->ev_p = nullptr;
   int lo = 0, hi = 0;
@@ -340,7 +383,7 @@ static void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspa
     double* Ajj = A + jj * kTile * ld + jj * kTile;
     double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;
     note_launch();
-    potrf_tile_kernel<<<1, 256, kPotrfSmemBytes, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
+    potrf_tile_kernel<<<1, 256, 0, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
     const int64_t below = n_pad - (jj + 1) * kTile;
     if (below <= 0) continue;
     double* panel = Ajj + kTile;  // rows below the diagonal tile, 128 columns
@@ -355,13 +398,6 @@ static void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspa
 // to their right.  As soon as (a) is done, panel J+1 is factored on a high-priority side stream
 // while (b) - where the flops are - keeps the SMs busy on the main stream.
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st) {
-  static bool attr_done[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_done[dev]) {
-    cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmemBytes);
-    attr_done[dev] = true;
-  }
   cudaMemsetAsync(ws.info, 0, sizeof(int), st);
   const int64_t nt = n_pad / kTile;
   const int64_t outer = 4;
