@@ -1,0 +1,9 @@
+/* SYNTAX-CHECK STUB ONLY - see ../Rinternals.h. */
+#ifndef COCONS_STUB_RDYNLOAD_H
+#define COCONS_STUB_RDYNLOAD_H
+typedef void* (*DL_FUNC)();
+typedef struct { const char* name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
+typedef struct _DllInfo DllInfo;
+int R_registerRoutines(DllInfo*, const void*, const R_CallMethodDef*, const void*, const void*);
+int R_useDynamicSymbols(DllInfo*, int);
+#endif

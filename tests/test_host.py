@@ -135,3 +135,27 @@ def test_device_bessel_header_on_host_against_mpmath(tmp_path):
             worst_m = max(worst_m, float(abs((mp.mpf(lib.h_m(nu, x)) - refm) / refm)))
     assert worst_k < 1e-14, worst_k
     assert worst_m < 3e-14, worst_m
+
+
+def test_r_glue_compiles_and_registers_the_reference_entry_points():
+    """rglue/cocons_glue.c replaces src/RcppExports.cpp: same .Call names and arities
+    (src/RcppExports.cpp:105-113) plus the fused entries; syntax-checked against the stub R API."""
+    glue = os.path.join(ROOT, "cocons_b200", "rglue")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-unused-parameter",
+                           "-I" + os.path.join(glue, "stub"), os.path.join(glue, "cocons_glue.c")])
+    text = open(os.path.join(glue, "cocons_glue.c")).read()
+    for name, nargs in (("_cocons_sumsmoothlone", 3), ("_cocons_cov_rns", 4), ("_cocons_cov_rns_pred", 6),
+                        ("_cocons_cov_rns_classic", 3), ("_cocons_cov_rns_taper_pred", 8),
+                        ("_cocons_cov_rns_taper", 6)):
+        assert '{"%s", (DL_FUNC)&%s, %d}' % (name, name, nargs) in text
+    assert "void R_init_cocons(DllInfo* dll)" in text
+    # every C-ABI function the glue calls is declared in the public header
+    called = set(re.findall(r"\b(cocons_[a-z0-9_]+)\s*\(", text))
+    assert called <= set(_header_symbols()) | {"cocons_ctx"}, called - set(_header_symbols())
+    rsrc = open(os.path.join(glue, "R", "cocons_b200.R")).read()
+    for fn in ("cov_rns <- function(theta, locs, x_covariates, smooth_limits)",
+               "cov_rns_pred <- function(theta, locs, locs_pred, x_covariates, x_covariates_pred, smooth_limits)",
+               "cov_rns_classic <- function(theta, locs, x_covariates)",
+               "GetNeg2loglikelihood <- function(theta, par.pos, locs, x_covariates, smooth.limits, z, n, lambda, "
+               "safe = TRUE)"):
+        assert fn in rsrc
