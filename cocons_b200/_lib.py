@@ -49,6 +49,21 @@ SIGNATURES = {
     "cocons_neg2loglik_dense": (ctypes.c_int, [ctypes.c_int, _i64, _i64, _i64, _i64, _dp, _dp, _dp, _dp, _dp, _dp,
                                                _dp, _dp, _dp, _dp, _ip]),
     "cocons_release_workspace": (None, []),
+    "cocons_dist_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i64, _i64, _i64, _dp, _dp, _dp, _vp,
+                                          ctypes.POINTER(_vp)]),
+    "cocons_dist_destroy": (None, [_vp]),
+    "cocons_dist_set_xbetas": (ctypes.c_int, [_vp, _i64, _dp]),
+    "cocons_dist_npanels": (_i64, [_vp]),
+    "cocons_dist_npad": (_i64, [_vp]),
+    "cocons_dist_panel_elems": (_i64, [_vp, _i64]),
+    "cocons_dist_assemble": (ctypes.c_int, [_vp, _dp, _dp, _dp]),
+    "cocons_dist_factor_panel": (ctypes.c_int, [_vp, _i64]),
+    "cocons_dist_pack_panel": (ctypes.c_int, [_vp, _i64, _vp]),
+    "cocons_dist_update": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64]),
+    "cocons_dist_fill_rhs": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ip]),
+    "cocons_dist_solve_block": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, ctypes.c_int]),
+    "cocons_dist_reduce_local": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "cocons_dist_perm": (ctypes.c_int, [_vp, _lp]),
     "cocons_bench_syrk": (ctypes.c_int, [ctypes.c_int, _i64, _i64, ctypes.c_int, _dp]),
 }
 

@@ -163,11 +163,22 @@ __device__ __forceinline__ void tri_decode(int64_t t, int& tr, int& tc) {
 template <int MODE>
 __global__ void __launch_bounds__(kAsmTile) assemble_lower_kernel(int64_t n, int64_t n_out, SiteTable T,
                                                                   double global_range, double nu_fixed,
-                                                                  double* __restrict__ C, int64_t ld) {
+                                                                  double* __restrict__ C, int64_t ld, int col_tile0,
+                                                                  int slab) {
+  // slab == 0: C is the whole matrix, blockIdx.x runs over its lower-triangle tiles.
+  // slab == 1: C holds only the tile columns [col_tile0, col_tile0 + gridDim.y) (a column panel of a
+  //            distributed matrix); blockIdx.x runs over the tile rows from col_tile0 down.
   __shared__ double cs[11][kAsmTile];
   __shared__ int corig[kAsmTile];
   int tr, tc;
-  tri_decode(blockIdx.x, tr, tc);
+  if (slab) {
+    tr = col_tile0 + blockIdx.x;
+    tc = col_tile0 + blockIdx.y;
+    if (tr < tc) return;
+    C -= (int64_t)col_tile0 * kAsmTile * ld;
+  } else {
+    tri_decode(blockIdx.x, tr, tc);
+  }
   const int tid = threadIdx.x;
   const int64_t I = (int64_t)tr * kAsmTile + tid;
   const int64_t J0 = (int64_t)tc * kAsmTile;
@@ -361,14 +372,30 @@ void launch_site_stage(int64_t n, int64_t n_fill, int p, const double* dX, int64
   site_stage_kernel<<<blocks, threads, 0, st>>>(n, n_fill, p, dX, ldx, dlocs, ldl, dtheta6, lim0, lim1, mode, T);
 }
 
+static void launch_assemble_any(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                                double* C, int64_t ld, int col_tile0, int slab, dim3 grid, cudaStream_t st);
+
 void launch_assemble_lower(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
                            double* C, int64_t ld, cudaStream_t st) {
   const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
-  const unsigned blocks = (unsigned)(nt * (nt + 1) / 2);
+  launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, C, ld, 0, 0, dim3((unsigned)(nt * (nt + 1) / 2)), st);
+}
+
+// column panel [col_tile0, col_tile0 + ncol_tiles) of the lower triangle into a slab whose first
+// column is tile column col_tile0 (rows keep their global index, leading dimension ld)
+void launch_assemble_panel(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                           double* slab, int64_t ld, int col_tile0, int ncol_tiles, cudaStream_t st) {
+  const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
+  launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, slab, ld, col_tile0, 1,
+                      dim3((unsigned)(nt - col_tile0), (unsigned)ncol_tiles), st);
+}
+
+static void launch_assemble_any(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                                double* C, int64_t ld, int col_tile0, int slab, dim3 grid, cudaStream_t st) {
   note_launch();
 #define COCONS_ASM_CASE(M)                                                                          \
   case M:                                                                                           \
-    assemble_lower_kernel<M><<<blocks, kAsmTile, 0, st>>>(n, n_out, T, global_range, nu_fixed, C, ld); \
+    assemble_lower_kernel<M><<<grid, kAsmTile, 0, st>>>(n, n_out, T, global_range, nu_fixed, C, ld, col_tile0, slab); \
     break;
   switch (mode) {
     COCONS_ASM_CASE(SM_GENERAL)

@@ -377,8 +377,8 @@ void chol_workspace_destroy(CholWorkspace* ws) {
 }
 
 // one outer panel: tiles [J0, J0+jb), every 128-wide step on stream `st`
-static void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws, int64_t J0, int64_t jb,
-                         cudaStream_t st) {
+void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws, int64_t J0, int64_t jb,
+                  cudaStream_t st) {
   for (int64_t jj = J0; jj < J0 + jb; ++jj) {
     double* Ajj = A + jj * kTile * ld + jj * kTile;
     double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;

@@ -67,6 +67,8 @@ void launch_site_stage(int64_t n, int64_t n_fill, int p, const double* dX, int64
                        cudaStream_t st);
 void launch_assemble_lower(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
                            double* C, int64_t ld, cudaStream_t st);
+void launch_assemble_panel(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                           double* slab, int64_t ld, int col_tile0, int ncol_tiles, cudaStream_t st);
 void launch_assemble_cross(int64_t m, int64_t n, SiteTable Tpred, SiteTable Ttrain, double global_range, double* C,
                            int64_t ld, cudaStream_t st);
 void launch_symmetrize(int64_t n, double* C, int64_t ld, cudaStream_t st);
@@ -81,6 +83,10 @@ struct CholWorkspace {
 };
 int chol_workspace_create(int64_t n_pad, CholWorkspace* ws);
 void chol_workspace_destroy(CholWorkspace* ws);
+// tiles [J0, J0+jb) of one outer panel (potrf + panel solve + in-panel update) on stream st; A is the
+// address element (0,0) of the full matrix would have (only columns of the panel are touched)
+void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws, int64_t J0, int64_t jb,
+                  cudaStream_t st);
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st);
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st);

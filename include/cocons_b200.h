@@ -150,6 +150,29 @@ int cocons_neg2loglik_dense(int kind, int64_t n, int64_t p, int64_t r, int64_t q
 /* release the per-process workspace of cocons_neg2loglik_dense */
 void cocons_release_workspace(void);
 
+/* ---- multi-GPU: one rank's half of the block-cyclic factorisation ------------------------
+ * For matrices beyond one GPU (n = 200 000).  One process per GPU; column panels of 512 are
+ * dealt round-robin to the ranks.  The exchange step (broadcast of a packed panel, small
+ * reductions in the solve) is issued by the host driver over NCCL on device buffers IT owns
+ * (cocons_b200/distributed.py; an R host would use the same calls from one worker per GPU).
+ * All `void*` arguments below are device pointers. */
+typedef struct cocons_dist cocons_dist;
+int cocons_dist_create(int device, int rank, int world, int64_t n, int64_t p, int64_t r, const double* locs,
+                       const double* x_covariates, const double* z, void* stream, cocons_dist** out);
+void cocons_dist_destroy(cocons_dist* ctx);
+int cocons_dist_set_xbetas(cocons_dist* ctx, int64_t q, const double* x_betas);
+int64_t cocons_dist_npanels(cocons_dist* ctx);
+int64_t cocons_dist_npad(cocons_dist* ctx);
+int64_t cocons_dist_panel_elems(cocons_dist* ctx, int64_t K);
+int cocons_dist_assemble(cocons_dist* ctx, const double* theta6, const double* smooth_limits, const double* mean_p);
+int cocons_dist_factor_panel(cocons_dist* ctx, int64_t K);
+int cocons_dist_pack_panel(cocons_dist* ctx, int64_t K, void* dst);
+int cocons_dist_update(cocons_dist* ctx, int64_t K, const void* src, int64_t J_lo, int64_t J_hi);
+int cocons_dist_fill_rhs(cocons_dist* ctx, int kind, void* rhs, int* nr_out);
+int cocons_dist_solve_block(cocons_dist* ctx, int64_t K, const void* bK, const void* tK, void* acc, void* Y, int nr);
+int cocons_dist_reduce_local(cocons_dist* ctx, const void* Y, int nr, void* out2, void* gram);
+int cocons_dist_perm(cocons_dist* ctx, int64_t* perm);
+
 /* ---- measurement helpers (bench.py) -------------------------------------
  * C (n x n, device-resident inside the call) -= A A' with the DMMA trailing-
  * update kernel, timed with CUDA events; returns milliseconds per repetition.

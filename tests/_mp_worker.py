@@ -1,0 +1,163 @@
+"""Worker of tests/test_multiproc.py: world-size-2 gloo run of the host-side multi-GPU logic with a
+numpy stand-in for the per-rank kernels (the CUDA kernels themselves are covered by -m gpu tests)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cocons_b200 import _lib  # noqa: E402
+from cocons_b200.distributed import PANEL, DistributedDenseLikelihood, _NoSync, fan_out  # noqa: E402
+from oracle import cov, rmirror  # noqa: E402
+
+
+class NumpyPanelOps(_NoSync):
+    """Same interface as CudaPanelOps, arithmetic in numpy/LAPACK on the local column panels."""
+
+    def __init__(self, locs, X, z, rank, world):
+        self.locs, self.X = np.asarray(locs, float), np.asarray(X, float)
+        self.n, self.p = self.X.shape
+        self.z = np.asarray(z, float).reshape(self.n, -1)
+        self.r = self.z.shape[1]
+        self.rank, self.world = rank, world
+        self.n_pad = (self.n + 127) // 128 * 128
+        self.npanels = (self.n_pad + PANEL - 1) // PANEL
+        self.cols = {}
+        self.info = 0
+        self.xb = None
+
+    def close(self):
+        pass
+
+    def width(self, K):
+        return min(PANEL, self.n_pad - K * PANEL)
+
+    def buffer(self, count):
+        return torch.zeros(max(int(count), 1), dtype=torch.float64)
+
+    def panel_elems(self, K):
+        return max(self.n_pad - (K + 1) * PANEL, 0) * self.width(K)
+
+    def set_xbetas(self, xb):
+        self.xb = np.asarray(xb, float).reshape(self.n, -1)
+
+    def assemble(self, theta6, limits, mean):
+        th = {k: np.array(theta6[i]) for i, k in enumerate(cov.ASPECTS)}
+        S = np.eye(self.n_pad)
+        S[: self.n, : self.n] = cov.cov_rns(th, self.locs, self.X, limits)
+        self.mean = None if mean is None else np.asarray(mean, float)
+        self.cols = {K: S[:, K * PANEL:K * PANEL + self.width(K)].copy()
+                     for K in range(self.rank, self.npanels, self.world)}
+
+    def factor_panel(self, K):
+        assert K % self.world == self.rank
+        c, r0, w = self.cols[K], K * PANEL, self.width(K)
+        try:
+            L = np.linalg.cholesky(c[r0:r0 + w, :])
+        except np.linalg.LinAlgError:
+            self.info = max(self.info, r0 + 1)
+            L = np.eye(w)
+        c[r0:r0 + w, :] = L
+        c[r0 + w:, :] = np.linalg.solve(L, c[r0 + w:, :].T).T
+
+    def pack_panel(self, K, buf):
+        rows = self.n_pad - (K + 1) * PANEL
+        if rows > 0:
+            buf.numpy()[: rows * self.width(K)] = self.cols[K][(K + 1) * PANEL:, :].ravel(order="F")
+
+    def update(self, K, buf, lo, hi):
+        rows = self.n_pad - (K + 1) * PANEL
+        if rows <= 0:
+            return
+        P = buf.numpy()[: rows * self.width(K)].reshape(rows, self.width(K), order="F")
+        for J in range(max(lo, K + 1), min(hi, self.npanels)):
+            if J % self.world != self.rank:
+                continue
+            off = J * PANEL - (K + 1) * PANEL
+            self.cols[J][J * PANEL:, :] -= P[off:, :] @ P[off:off + self.width(J), :].T
+
+    def fill_rhs(self, kind, rhs):
+        zc = self.z - (self.X @ self.mean)[:, None] if (kind == _lib.ML and self.mean is not None) else self.z
+        blocks = [zc]
+        if kind == _lib.PROFILE:
+            blocks = [self.xb, self.z]
+        elif kind == _lib.REML:
+            blocks = [self.X, self.z]
+        B = np.zeros((self.npanels * PANEL, sum(b.shape[1] for b in blocks)))
+        B[: self.n] = np.column_stack(blocks)
+        nr = B.shape[1]
+        rhs.numpy()[:] = B.reshape(self.npanels, PANEL, nr).transpose(0, 2, 1).ravel()
+        return nr
+
+    def solve_block(self, K, bK, tK, acc, Y, nr):
+        w, r0 = self.width(K), K * PANEL
+        b = (bK.numpy() - tK.numpy()).reshape(nr, PANEL).T[:w]
+        y = np.linalg.solve(np.tril(self.cols[K][r0:r0 + w, :]), b)
+        Yv = Y.numpy().reshape(nr, self.n_pad).T
+        Yv[r0:r0 + w] = y
+        below = self.cols[K][r0 + w:, :] @ y
+        A = acc.numpy().reshape(self.npanels, nr, PANEL)
+        for t in range(below.shape[0]):
+            g = r0 + w + t
+            A[g // PANEL, :, g % PANEL] += below[t]
+
+    def reduce_local(self, Y, nr, out2, gram):
+        s = 0.0
+        for K, c in self.cols.items():
+            d = np.diag(c[K * PANEL:K * PANEL + self.width(K), :])
+            g = K * PANEL + np.arange(self.width(K))
+            s += np.sum(np.log(d[g < self.n]))
+        Yv = Y.numpy().reshape(nr, self.n_pad).T[: self.n]
+        out2.numpy()[:] = [s, self.info]
+        gram.numpy()[:] = (Yv.T @ Yv).ravel()
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(11)
+    n, p = 1100, 3  # 1152 padded rows = 3 panels (512, 512, 128): ragged last panel, uneven ownership
+    locs = rng.uniform(-1, 1, (n, 2))
+    X = rmirror.get_scale(np.column_stack([np.ones(n), rng.standard_normal((n, p - 1))]))["std.covs"]
+    z = rng.standard_normal((n, 2))
+    tl = {"mean": np.array([0.1, 0.3, -0.2]), "std.dev": np.array([0.2, 0.15, 0.1]),
+          "scale": np.array([-1.6, 0.2, -0.15]), "aniso": np.array([0.1, 0.2, -0.1]),
+          "tilt": np.array([0.3, -0.2, 0.1]), "smooth": np.array([0.2, 0.3, -0.2]), "nugget": np.array([-4, 0.1, 0.1])}
+    lim = [0.5, 2.5]
+    res = {}
+    with DistributedDenseLikelihood(locs, X, z, ops=NumpyPanelOps(locs, X, z, rank, world)) as d:
+        t = d.terms(_lib.ML, tl, lim, tl["mean"])
+        res["ml"] = [t["logdet"]] + list(t["quad"])
+        d.set_xbetas(X[:, :2])
+        t = d.terms(_lib.PROFILE, tl, lim)
+        res["profile"] = [t["logdet"], t["logdet_w"]] + list(t["quad"])
+        try:
+            # fixed non-half-integer smoothness makes Sigma singular
+            d.terms(_lib.ML, dict(tl, smooth=np.zeros(3)), [1.0, 1.0])
+            res["notpd"] = False
+        except Exception as e:  # noqa: BLE001
+            res["notpd"] = type(e).__name__
+    # regime 1: fan-out of independent evaluations
+    pts = [0.1 * k for k in range(7)]
+    res["fan"] = fan_out(pts, lambda x: x * x + rank * 0.0)
+    if rank == 0:
+        S = cov.cov_rns(tl, locs, X, lim)
+        R = rmirror.r_chol(S)
+        y = rmirror._fwd(R, z - (X @ tl["mean"])[:, None])
+        res["ml_ref"] = [float(np.sum(np.log(np.diag(R))))] + list((y * y).sum(axis=0))
+        Yx, yz = rmirror._fwd(R, X[:, :2]), rmirror._fwd(R, z)
+        W, b = Yx.T @ Yx, Yx.T @ yz
+        quad = (yz * yz).sum(axis=0) - np.einsum("ij,ij->j", b, np.linalg.solve(W, b))
+        res["profile_ref"] = [float(np.sum(np.log(np.diag(R)))), float(np.sum(np.log(np.diag(np.linalg.cholesky(W)))))] \
+            + list(quad)
+        print("RESULT " + json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

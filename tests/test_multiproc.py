@@ -1,0 +1,28 @@
+"""World-size-2 gloo run (CPU) of the multi-GPU host logic: panel ownership, look-ahead order,
+the per-panel reduce of the distributed solve, the final all-reduces and the evaluation fan-out."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world_size_two_matches_single_process_reference():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    procs = []
+    for rank in range(2):
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_mp_worker.py")],
+                                      env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-3000:]
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT ")][0]
+    res = json.loads(line[len("RESULT "):])
+    assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-10, atol=0)
+    assert np.allclose(res["profile"], res["profile_ref"], rtol=1e-9, atol=0)
+    assert res["notpd"] == "NotPositiveDefinite"
+    assert np.allclose(res["fan"], [(0.1 * k) ** 2 for k in range(7)])
