@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--n", type=int, default=50000, help="sites (the metric is quoted at 50 000)")
+    ap.add_argument("--sites", dest="n", type=int, default=50000, help="sites (the metric is quoted at 50 000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run: device-resident arm only (no DGEMM probe, no e2e leg, no CPU sample)")

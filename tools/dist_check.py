@@ -19,7 +19,7 @@ from cocons_b200.distributed import DistributedDenseLikelihood  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--sites", dest="n", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
