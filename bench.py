@@ -219,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - cocons_b200 has no CPU path to fall back to")
     torch.cuda.set_device(local_rank)
+    os.environ["COCONS_DEVICE"] = str(local_rank)  # device of the one-shot (host-buffer) entry point
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
