@@ -11,6 +11,7 @@
 //                       SYRK update
 //   chol_factor         two-level driver: 128-wide steps inside 512-wide panels
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/cocons_b200.h"
 #include "common.cuh"
@@ -32,10 +33,12 @@ namespace cocons {
 constexpr int GBM = 128, GBK = 16, GSTAGES = 4;
 constexpr int GLDA = GBM + 4;  // padded leading dimension of a shared k-row (== 4 mod 16: conflict-free LDS.128)
 
-template <int BN>
+template <int BN, int NU = 4>
 struct GemmCfg {
-  static constexpr int kWarpsJ = BN / 32;            // warp tile is 64(i) x 32(j)
-  static constexpr int kThreads = 2 * kWarpsJ * 32;  // 2 warps along i
+  static constexpr int kWarpI = 16 * NU;             // warp tile is (16 NU)(i) x 32(j): NU = 4 -> 64, NU = 2 -> 32
+  static constexpr int kWarpsI = GBM / kWarpI;
+  static constexpr int kWarpsJ = BN / 32;
+  static constexpr int kThreads = kWarpsI * kWarpsJ * 32;
   static constexpr int kLdb = BN + 4;
   static constexpr int kStageDoubles = GBK * (GLDA + kLdb);
   static constexpr int kSmemBytes = GSTAGES * kStageDoubles * (int)sizeof(double);
@@ -43,6 +46,8 @@ struct GemmCfg {
   // one runs its main loop while the other is in its prologue / read-modify-write epilogue
   static constexpr int kMinBlocks = (BN == 64) ? 2 : 1;
 };
+// BN = 64, NU = 2: 8 warps of 32 x 32 per CTA (<= 128 registers), two CTAs per SM = 4 warps per
+// scheduler, so that two warps are left to interleave DMMAs while others wait on LDS / barriers.
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -79,72 +84,98 @@ __device__ __forceinline__ void trapezoid_decode(int64_t t, int ni, int& bi, int
   bi = c + (int)(rem % per);
 }
 
-template <int BN, int ASSIGN>
-__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, GemmCfg<BN>::kMinBlocks)
+template <int BN, int NU, int ASSIGN>
+__global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kMinBlocks)
     gemm_nt_kernel(int ni, int nj, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                   int64_t ldc, int lower_only) {
-  using Cfg = GemmCfg<BN>;
+                   int64_t ldc, int lower_only, int64_t ntiles, int dbg) {
+  // Persistent: CTA b walks tiles b, b + gridDim.x, ... and keeps ONE cp.async pipeline running across
+  // tile boundaries, so the first stages of the next tile are already in flight while the
+  // read-modify-write epilogue of the current one runs.
+  using Cfg = GemmCfg<BN, NU>;
   extern __shared__ __align__(16) double smem[];
-  int bi, bj;
-  if (lower_only) {
-    trapezoid_decode<GBM / BN>(blockIdx.x, ni, bi, bj);
-  } else {
-    bj = blockIdx.x / ni;
-    bi = blockIdx.x - bj * ni;
-  }
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, c4 = lane & 3;
-  const int iw = (warp & 1) * 64, jw = (warp >> 1) * 32;
-  const double* Ag = A + (int64_t)bi * GBM;
-  const double* Bg = B + (int64_t)bj * BN;
+  const int iw = (warp % Cfg::kWarpsI) * Cfg::kWarpI, jw = (warp / Cfg::kWarpsI) * 32;
 
+  auto decode = [&](int64_t t, int& bi, int& bj) {
+    if (lower_only) {
+      trapezoid_decode<GBM / BN>(t, ni, bi, bj);
+    } else {
+      bj = (int)(t / ni);
+      bi = (int)(t - (int64_t)bj * ni);
+    }
+  };
   auto As = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles; };
   auto Bs = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles + GBK * GLDA; };
 
-  auto load_stage = [&](int s, int64_t kb) {
-    double* as = As(s);
-    double* bs = Bs(s);
+  const int64_t nkb = K / GBK;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_tiles = (ntiles > first) ? (ntiles - first + stride - 1) / stride : 0;
+  const int64_t total = my_tiles * nkb;
+
+  // loader state: which (tile, k-block) the next cp.async stage belongs to
+  int64_t ld_it = 0, ld_tile = 0, ld_kb = 0;
+  const double* ld_A = A;
+  const double* ld_B = B;
+  auto issue_load = [&]() {
+    if (ld_it < total) {
+      if (ld_kb == 0) {
+        int bi, bj;
+        decode(first + ld_tile * stride, bi, bj);
+        ld_A = A + (int64_t)bi * GBM;
+        ld_B = B + (int64_t)bj * BN;
+      }
+      double* as = As((int)(ld_it % GSTAGES));
+      double* bs = Bs((int)(ld_it % GSTAGES));
 #pragma unroll
-    for (int c = tid; c < GBK * (GBM / 2); c += Cfg::kThreads) {
-      const int k = c / (GBM / 2), i2 = c % (GBM / 2);
-      cp_async16(as + k * GLDA + 2 * i2, Ag + (kb * GBK + k) * lda + 2 * i2);
-    }
+      for (int c = tid; c < GBK * (GBM / 2); c += Cfg::kThreads) {
+        const int k = c / (GBM / 2), i2 = c % (GBM / 2);
+        cp_async16(as + k * GLDA + 2 * i2, ld_A + (ld_kb * GBK + k) * lda + 2 * i2);
+      }
 #pragma unroll
-    for (int c = tid; c < GBK * (BN / 2); c += Cfg::kThreads) {
-      const int k = c / (BN / 2), j2 = c % (BN / 2);
-      cp_async16(bs + k * Cfg::kLdb + 2 * j2, Bg + (kb * GBK + k) * ldb + 2 * j2);
+      for (int c = tid; c < GBK * (BN / 2); c += Cfg::kThreads) {
+        const int k = c / (BN / 2), j2 = c % (BN / 2);
+        cp_async16(bs + k * Cfg::kLdb + 2 * j2, ld_B + (ld_kb * GBK + k) * ldb + 2 * j2);
+      }
+      ++ld_it;
+      if (++ld_kb == nkb) ld_kb = 0, ++ld_tile;
     }
+    cp_async_commit();
   };
 
-  double acc[4][8][2];
+  double acc[4][2 * NU][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int b = 0; b < 2 * NU; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  const int64_t nkb = K / GBK;
 #pragma unroll
-  for (int s = 0; s < GSTAGES - 1; ++s) {
-    if (s < nkb) load_stage(s, s);
-    cp_async_commit();
-  }
-  for (int64_t kb = 0; kb < nkb; ++kb) {
-    cp_async_wait<GSTAGES - 2>();
-    __syncthreads();
-    {
-      const int64_t nxt = kb + GSTAGES - 1;
-      if (nxt < nkb) load_stage((int)(nxt % GSTAGES), nxt);
-      cp_async_commit();
+  for (int s = 0; s < GSTAGES - 1; ++s) issue_load();
+
+  int64_t kb = 0, tile = 0;
+  double* Cg = nullptr;
+  for (int64_t it = 0; it < total; ++it) {
+    if (kb == 0) {
+      int bi, bj;
+      decode(first + tile * stride, bi, bj);
+      Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
+      if (!ASSIGN) {  // pull the C tile towards L2 while the main loop runs
+        for (int l = tid; l < BN * 8; l += Cfg::kThreads)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + (int64_t)(l >> 3) * ldc + (l & 7) * 16));
+      }
     }
-    const double* as = As((int)(kb % GSTAGES)) + iw + 2 * g;
-    const double* bs = Bs((int)(kb % GSTAGES)) + jw + 2 * g;
+    cp_async_wait<GSTAGES - 2>();
+    if (!(dbg & 4)) __syncthreads();
+    if (!(dbg & 2)) issue_load(); else cp_async_commit();
+    const double* as = As((int)(it % GSTAGES)) + iw + 2 * g;
+    const double* bs = Bs((int)(it % GSTAGES)) + jw + 2 * g;
 #pragma unroll
     for (int kk = 0; kk < GBK / 4; ++kk) {
       const int k = kk * 4 + c4;
-      double fi[8], fj[4];
+      double fi[2 * NU], fj[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const double2 v = *reinterpret_cast<const double2*>(as + k * GLDA + 16 * u);
         fi[2 * u] = v.x;
         fi[2 * u + 1] = v.y;
@@ -158,18 +189,187 @@ __global__ void __launch_bounds__(GemmCfg<BN>::kThreads, GemmCfg<BN>::kMinBlocks
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
+        for (int b = 0; b < 2 * NU; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
+    }
+    if (++kb == nkb && (dbg & 1)) { kb = 0; ++tile; if (it + 1 == total) C[tid] = acc[0][0][0] + acc[3][1][1]; }
+    else if (kb == nkb) {
+      // epilogue: a thread owns rows r0..r0+3 of column j for every (a, u)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int j = jw + 16 * (a >> 1) + 2 * g + (a & 1);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int r0 = iw + 16 * u + 4 * c4;
+          double2* p = reinterpret_cast<double2*>(Cg + (int64_t)j * ldc + r0);
+          double2 lo, hi;
+          if (ASSIGN) {
+            lo.x = acc[a][2 * u][0];
+            lo.y = acc[a][2 * u + 1][0];
+            hi.x = acc[a][2 * u][1];
+            hi.y = acc[a][2 * u + 1][1];
+          } else {
+            lo = p[0];
+            hi = p[1];
+            lo.x -= acc[a][2 * u][0];
+            lo.y -= acc[a][2 * u + 1][0];
+            hi.x -= acc[a][2 * u][1];
+            hi.y -= acc[a][2 * u + 1][1];
+          }
+          p[0] = lo;
+          p[1] = hi;
+          acc[a][2 * u][0] = acc[a][2 * u + 1][0] = acc[a][2 * u][1] = acc[a][2 * u + 1][1] = 0.0;
+        }
+      }
+      kb = 0;
+      ++tile;
     }
   }
   cp_async_wait<0>();
+}
 
-  // epilogue: a thread owns rows r0..r0+3 of column j for every (a, u)
+// ---------------------------------------------------------------------------
+// Same tile computation, operands fed by the bulk-copy (TMA) engine instead of per-thread LDGSTS.
+// One elected lane issues, per stage, 32 `cp.async.bulk` row copies (16 k-rows of A and of B, each a
+// contiguous 1 KB / BN*8 B segment of a matrix column) straight into the padded shared rows; the
+// bytes land on an mbarrier (`complete_tx`).  Consumers wait on that barrier and hand the slot back
+// through an `empty` mbarrier - no __syncthreads, no cp.async.wait_group, no per-thread address
+// arithmetic in the MMA warps.  The producer role rotates over the warps (stage s is issued by warp
+// s mod nwarps) so that no warp is permanently behind.  One tile per CTA, two CTAs per SM.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int BN, int NU, int ASSIGN>
+__global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kMinBlocks)
+    gemm_nt_tma_kernel(int ni, int nj, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
+                       double* C, int64_t ldc, int lower_only) {
+  using Cfg = GemmCfg<BN, NU>;
+  constexpr int kWarps = Cfg::kThreads / 32;
+  constexpr uint32_t kStageBytes = GBK * (GBM + BN) * (uint32_t)sizeof(double);
+  extern __shared__ __align__(16) double smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)GSTAGES * Cfg::kStageDoubles);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c4 = lane & 3;
+  const int iw = (warp % Cfg::kWarpsI) * Cfg::kWarpI, jw = (warp / Cfg::kWarpsI) * 32;
+  int bi, bj;
+  if (lower_only) {
+    trapezoid_decode<GBM / BN>(blockIdx.x, ni, bi, bj);
+  } else {
+    bj = blockIdx.x / ni;
+    bi = blockIdx.x - bj * ni;
+  }
+  const double* Ag = A + (int64_t)bi * GBM;
+  const double* Bg = B + (int64_t)bj * BN;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + GSTAGES);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t nkb = K / GBK;
+  const uint32_t stage0 = smem_u32(smem);
+  auto produce = [&](int64_t ld) {  // one lane
+    const int slot = (int)(ld % GSTAGES);
+    const int64_t fill = ld / GSTAGES;
+    if (fill >= 1) mbar_wait(empty0 + 8 * slot, (uint32_t)((fill - 1) & 1));
+    const uint32_t fb = full0 + 8 * slot;
+    mbar_expect_tx(fb, kStageBytes);
+    const uint32_t da = stage0 + (uint32_t)slot * Cfg::kStageDoubles * 8u;
+    const uint32_t db = da + GBK * GLDA * 8u;
+    const double* a = Ag + ld * GBK * lda;
+    const double* b = Bg + ld * GBK * ldb;
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) bulk_g2s(da + k * GLDA * 8u, a + (int64_t)k * lda, GBM * 8u, fb);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) bulk_g2s(db + k * Cfg::kLdb * 8u, b + (int64_t)k * ldb, BN * 8u, fb);
+  };
+
+  double acc[4][2 * NU][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 2 * NU; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  if (!ASSIGN) {  // pull the C tile towards L2 while the main loop runs
+    const double* Cp = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
+    for (int l = tid; l < BN * 8; l += Cfg::kThreads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + (int64_t)(l >> 3) * ldc + (l & 7) * 16));
+  }
+  if (warp == 0 && lane == 0)
+    for (int s = 0; s < GSTAGES - 1 && s < nkb; ++s) produce(s);
+  __syncwarp();
+
+  for (int64_t it = 0; it < nkb; ++it) {
+    const int64_t ld = it + GSTAGES - 1;
+    if (ld < nkb && warp == (int)(it % kWarps) && lane == 0) produce(ld);
+    __syncwarp();
+    const int slot = (int)(it % GSTAGES);
+    mbar_wait(full0 + 8 * slot, (uint32_t)((it / GSTAGES) & 1));
+    const double* as = smem + (size_t)slot * Cfg::kStageDoubles + iw + 2 * g;
+    const double* bs = smem + (size_t)slot * Cfg::kStageDoubles + GBK * GLDA + jw + 2 * g;
+#pragma unroll
+    for (int kk = 0; kk < GBK / 4; ++kk) {
+      const int k = kk * 4 + c4;
+      double fi[2 * NU], fj[4];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const double2 v = *reinterpret_cast<const double2*>(as + k * GLDA + 16 * u);
+        fi[2 * u] = v.x;
+        fi[2 * u + 1] = v.y;
+      }
+#pragma unroll
+      for (int v2 = 0; v2 < 2; ++v2) {
+        const double2 v = *reinterpret_cast<const double2*>(bs + k * Cfg::kLdb + 16 * v2);
+        fj[2 * v2] = v.x;
+        fj[2 * v2 + 1] = v.y;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2 * NU; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+  }
+
   double* Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int j = jw + 16 * (a >> 1) + 2 * g + (a & 1);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
       const int r0 = iw + 16 * u + 4 * c4;
       double2* p = reinterpret_cast<double2*>(Cg + (int64_t)j * ldc + r0);
       double2 lo, hi;
@@ -198,27 +398,56 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return;
   static bool attr_done[16] = {};
+  static int variant = -1, dbg = 0;
+  if (variant < 0) {
+    const char* d = getenv("COCONS_GEMM_DEBUG");  // timing experiments only (results are wrong when set)
+    dbg = d ? atoi(d) : 0;
+    const char* e = getenv("COCONS_GEMM_VARIANT");  // tuning knob: 0/1 = LDGSTS feed (4 warps of 64x32 / 8 warps of 32x32), 2/3 = bulk-copy (TMA) feed, same shapes; default 3
+    variant = e ? atoi(e) : 3;
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
-    cudaFuncSetAttribute(gemm_nt_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_nt_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_kernel<64, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<64, 4>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<64, 2>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_kernel<128, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<128, 4>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<64, 4>::kSmemBytes + 64);
+    cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<64, 2>::kSmemBytes + 64);
     attr_done[dev] = true;
   }
+  static int num_sms[16] = {};
+  if (dev < 16 && num_sms[dev] == 0) cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  const int sms = (dev < 16 && num_sms[dev] > 0) ? num_sms[dev] : 148;
   const int ni = (int)(M / GBM);
   note_launch();
   if (mode == 1) {
     const int nj = (int)(N / 128);
     const int64_t tiles = lower_only ? ((int64_t)nj * ni - (int64_t)nj * (nj - 1) / 2) : (int64_t)ni * nj;
-    gemm_nt_kernel<128, 1><<<(unsigned)tiles, GemmCfg<128>::kThreads, GemmCfg<128>::kSmemBytes, st>>>(
-        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+    gemm_nt_kernel<128, 4, 1><<<grid, GemmCfg<128, 4>::kThreads, GemmCfg<128, 4>::kSmemBytes, st>>>(
+        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
   } else {
     const int nj = (int)(N / 64);
     const int ng = (int)(N / 128);  // column groups sharing a diagonal block
     const int64_t tiles = lower_only ? 2 * ((int64_t)ng * ni - (int64_t)ng * (ng - 1) / 2) : (int64_t)ni * nj;
-    gemm_nt_kernel<64, 0><<<(unsigned)tiles, GemmCfg<64>::kThreads, GemmCfg<64>::kSmemBytes, st>>>(
-        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)sms);
+    if (variant == 2)
+      gemm_nt_tma_kernel<64, 4, 0><<<(unsigned)tiles, GemmCfg<64, 4>::kThreads, GemmCfg<64, 4>::kSmemBytes + 64, st>>>(
+          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+    else if (variant == 3)
+      gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64, st>>>(
+          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
+    else if (variant == 1)
+      gemm_nt_kernel<64, 2, 0><<<grid, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes, st>>>(
+          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
+    else
+      gemm_nt_kernel<64, 4, 0><<<grid, GemmCfg<64, 4>::kThreads, GemmCfg<64, 4>::kSmemBytes, st>>>(
+          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
   }
 }
 

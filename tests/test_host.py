@@ -41,7 +41,8 @@ def test_library_is_sm100a_dmma_code():
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass  # FP64 tensor-core trailing update
-    assert "LDGSTS" in sass  # async global->shared operand feed
+    assert "UBLKCP" in sass  # bulk-copy (TMA) operand feed of the trailing update
+    assert "SYNCS.ARRIVE.TRANS64" in sass  # mbarrier expect_tx / complete_tx pipeline
 
 
 def test_sumsmoothlone_matches_oracle():
