@@ -17,7 +17,7 @@
 #include <math.h>
 
 #ifdef __CUDACC__
-#define COCONS_HD __host__ __device__ __forceinline__
+#define COCONS_HD __device__ __forceinline__
 #else
 #define COCONS_HD inline
 #endif
@@ -29,9 +29,9 @@ namespace cocons {
 constexpr double kPi = 3.141592653589793238462643383279502884;
 constexpr double kHalfPi = 1.570796326794896619231321691639751442;
 constexpr double kBesselEps = 1.0e-16;  // series / continued-fraction stopping level
-constexpr double kHankelX = 25.0;       // Hankel tail used for x >= kHankelX and nu <= kHankelNuMax
-constexpr double kHankelNuMax = 3.0;    // (14 terms reach 8.8e-16 there)
-constexpr int kHankelTerms = 14;
+constexpr double kHankelX = 18.0;       // Hankel tail used for x >= kHankelX and nu <= kHankelNuMax
+constexpr double kHankelNuMax = 3.0;    // (terms shrink until k ~ 2x: ~4e-15 at x = 18, 9e-16 from x = 25 on)
+constexpr int kHankelTerms = 40;
 
 // gamma1, gamma2, 1/Gamma(1+mu), 1/Gamma(1-mu) for |mu| <= 1/2
 struct TemmeGammas {
@@ -96,30 +96,52 @@ COCONS_HD void bessel_k_temme(double mu, double x, const TemmeGammas& G, double&
   kmu1 = sum1 * (2.0 / x);
 }
 
-// e^x K_mu(x), e^x K_{mu+1}(x) for x > 2, |mu| <= 1/2  (Steed's algorithm for CF2)
+// reciprocals 1/i for the CF2 recurrence (uniform index: constant-cache broadcast on the device)
+#ifdef __CUDACC__
+__constant__
+#else
+static const
+#endif
+    double kInvInt[128] = {
+        0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12,
+        1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23,
+        1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34,
+        1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45,
+        1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56,
+        1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63, 1.0 / 64, 1.0 / 65, 1.0 / 66, 1.0 / 67,
+        1.0 / 68, 1.0 / 69, 1.0 / 70, 1.0 / 71, 1.0 / 72, 1.0 / 73, 1.0 / 74, 1.0 / 75, 1.0 / 76, 1.0 / 77, 1.0 / 78,
+        1.0 / 79, 1.0 / 80, 1.0 / 81, 1.0 / 82, 1.0 / 83, 1.0 / 84, 1.0 / 85, 1.0 / 86, 1.0 / 87, 1.0 / 88, 1.0 / 89,
+        1.0 / 90, 1.0 / 91, 1.0 / 92, 1.0 / 93, 1.0 / 94, 1.0 / 95, 1.0 / 96, 1.0 / 97, 1.0 / 98, 1.0 / 99, 1.0 / 100,
+        1.0 / 101, 1.0 / 102, 1.0 / 103, 1.0 / 104, 1.0 / 105, 1.0 / 106, 1.0 / 107, 1.0 / 108, 1.0 / 109, 1.0 / 110,
+        1.0 / 111, 1.0 / 112, 1.0 / 113, 1.0 / 114, 1.0 / 115, 1.0 / 116, 1.0 / 117, 1.0 / 118, 1.0 / 119, 1.0 / 120,
+        1.0 / 121, 1.0 / 122, 1.0 / 123, 1.0 / 124, 1.0 / 125, 1.0 / 126, 1.0 / 127};
+
+// e^x K_mu(x), e^x K_{mu+1}(x) for x > 2, |mu| <= 1/2  (Steed's algorithm for CF2).
+// Thompson-Barnett's q / c recurrences are folded into one division-free three-term recurrence on
+// the summand p_i = c_i q_i:   p_i = (b_i p_{i-1} + a_{i-1}/(i-1) p_{i-2}) / i,  a_i = -(1/4 - mu^2) - i(i-1),
+// so that the only division left per step is the continued-fraction update d = 1/(b + a d).
 COCONS_HD void bessel_k_cf2_scaled(double mu, double x, double& kmu, double& kmu1) {
-  const double mu2 = mu * mu;
+  const double a1 = 0.25 - mu * mu;
   double b = 2.0 * (1.0 + x);
   double d = 1.0 / b;
   double h = d, delh = d;
-  double q1 = 0.0, q2 = 1.0;
-  const double a1 = 0.25 - mu2;
-  double q = a1, c = a1;
-  double a = -a1;
-  double s = fma(q, delh, 1.0);
-  for (int i = 2; i < 512; ++i) {
-    a -= (double)(2 * (i - 1));
-    c = -a * c / (double)i;
-    const double qnew = fma(-b, q2, q1) / a;
-    q1 = q2;
-    q2 = qnew;
-    q = fma(c, qnew, q);
+  double p_prev = 0.0, p_cur = a1;  // p_0, p_1
+  double qsum = a1;
+  double s = fma(qsum, delh, 1.0);
+  double a_prev = -a1;  // a_1
+  for (int i = 2; i < 128; ++i) {
+    const double a = a_prev - (double)(2 * (i - 1));  // a_i
+    const double p_new = fma(b, p_cur, a_prev * kInvInt[i - 1] * p_prev) * kInvInt[i];
+    p_prev = p_cur;
+    p_cur = p_new;
+    qsum += p_new;
     b += 2.0;
     d = 1.0 / fma(a, d, b);
     delh = fma(b, d, -1.0) * delh;
     h += delh;
-    const double dels = q * delh;
+    const double dels = qsum * delh;
     s += dels;
+    a_prev = a;
     if (fabs(dels) < fabs(s) * kBesselEps) break;
   }
   h = a1 * h;
@@ -127,16 +149,19 @@ COCONS_HD void bessel_k_cf2_scaled(double mu, double x, double& kmu, double& kmu
   kmu1 = kmu * (mu + x + 0.5 - h) / x;
 }
 
-// e^x K_nu(x) from the Hankel expansion, x >= kHankelX, 0 < nu <= kHankelNuMax
+// e^x K_nu(x) from the Hankel expansion, x >= kHankelX, 0 < nu <= kHankelNuMax; summed until the
+// terms drop below 1e-17 of the sum (14 terms at x = 25, ~36 at x = 18)
 COCONS_HD double bessel_k_hankel_scaled(double nu, double x) {
   const double four_nu2 = 4.0 * nu * nu;
   const double r8x = 1.0 / (8.0 * x);
   double term = 1.0, sum = 1.0;
-#pragma unroll
   for (int k = 1; k <= kHankelTerms; ++k) {
     const double odd = (double)(2 * k - 1);
-    term *= (four_nu2 - odd * odd) * r8x * (1.0 / (double)k);
+    const double next = term * (four_nu2 - odd * odd) * r8x * kInvInt[k];
+    if (fabs(next) > fabs(term)) break;  // asymptotic series: stop at the smallest term
+    term = next;
     sum += term;
+    if (fabs(term) < 1e-17 * fabs(sum)) break;
   }
   return sqrt(kHalfPi / x) * sum;
 }
