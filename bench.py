@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
     values = []
     for s in range(args.warmup):
         t = ctx.terms(_lib.ML, theta_at(s, rank), LIMITS, THETA["mean"])
-    phases = {"assembly_ms": [], "factor_ms": [], "solve_ms": []}
+    phases = {"assembly_ms": [], "factor_ms": [], "solve_ms": [], "kernel_ms": []}
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -300,7 +300,22 @@ def run_ours(args, rank, world, local_rank):
         return
     value = world * args.steps / elapsed
     f_ms = float(np.mean(phases["factor_ms"]))
-    achieved = flops_chol(n) / (f_ms * 1e-3) / 1e12
+    phase_tflops = flops_chol(n) / (f_ms * 1e-3) / 1e12
+    # dominant kernel: the largest trailing-update launch of each factorisation (C -= P P^T on the
+    # (n_pad - 1024)^2 lower triangle, K = 512), bracketed by CUDA events inside the timed region
+    n_pad = (n + 127) // 128 * 128
+    rest = n_pad - 1024
+    kernel_flops = rest * (rest + 1) / 2 * 2 * 512  # algorithmic: lower triangle incl. diagonal
+    k_ms = float(np.mean(phases["kernel_ms"]))
+    achieved = kernel_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_tma_ncu_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("n") == n:
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     cpu = cpu_reference_sample(n) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": "neg2loglik evals/sec (assembly+Cholesky) at n=50k", "value": value, "unit": "evals/s",
@@ -310,15 +325,23 @@ def run_ours(args, rank, world, local_rank):
                    "n": n, "p": p, "r": 1, "parallelism": "replicas x%d (one theta per GPU, no collective)" % world,
                    "l2": "working set %.1f GB per evaluation >> 126 MB L2; no flush needed" % (8e-9 * n * n),
                    "objective_value_step0": values[0]},
-        "phases_ms": {k: float(np.mean(v)) for k, v in phases.items()},
+        "phases_ms": {k: float(np.mean(v)) for k, v in phases.items() if k != "kernel_ms"},
         "assembly_pairs_per_s": n * (n - 1) / 2 / (float(np.mean(phases["assembly_ms"])) * 1e-3),
-        "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (DMMA.8x8x4 trailing update) + panel kernels = "
-                                                  "Cholesky phase", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "tensor",
+                     "kernel": "gemm_nt_tma_kernel<64,2,0> (DMMA.8x8x4 trailing update, bulk-copy fed): the largest "
+                               "launch of each factorisation, %d^2 lower triangle x K=512" % rest,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if (peak and achieved) else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flops_per_launch": kernel_flops, "launch_ms": k_ms,
                      "peak_source": "same-run cuBLAS dgemm 8192^3 (torch.matmul float64), burst; "
                                     "MEASURED_PEAKS.json has no FP64 entry",
-                     "derived_peak": DERIVED_FP64_PEAK_TFLOPS, "frac_of_derived": achieved / DERIVED_FP64_PEAK_TFLOPS,
-                     "algorithmic_flops_per_eval": flops_chol(n)},
+                     "derived_peak": DERIVED_FP64_PEAK_TFLOPS,
+                     "frac_of_derived": achieved / DERIVED_FP64_PEAK_TFLOPS if achieved else None,
+                     "dmma_pipe_peak": 36.9,  # tools/micro/dmma_peak.cu on this pool (register-only DMMA loop)
+                     "cholesky_phase": {"achieved": phase_tflops, "frac": phase_tflops / peak if peak else None,
+                                        "frac_of_derived": phase_tflops / DERIVED_FP64_PEAK_TFLOPS,
+                                        "algorithmic_flops_per_eval": flops_chol(n), "ms": f_ms}},
         "e2e": {"value": world * args.steps / e2e_elapsed, "unit": "evals/s",
                 "h2d_bytes_per_step": int(8 * (n * 2 + n * p + n + 7 * p)), "d2h_bytes_per_step": int(8 * 2 + 4)},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -280,7 +280,10 @@ class DenseLikelihood:
     def timings(self):
         ms = np.empty(4)
         _lib.lib().cocons_ctx_timings(self._h, _lib.ptr(ms))
-        return {"assembly_ms": ms[0], "factor_ms": ms[1], "solve_ms": ms[2], "total_ms": ms[3]}
+        kms, kfl = _lib.ctypes.c_double(), _lib.ctypes.c_double()
+        _lib.lib().cocons_ctx_kernel_timing(self._h, _lib.ctypes.byref(kms), _lib.ctypes.byref(kfl))
+        return {"assembly_ms": ms[0], "factor_ms": ms[1], "solve_ms": ms[2], "total_ms": ms[3],
+                "kernel_ms": kms.value, "kernel_flops": kfl.value}
 
 
 # --------------------------------------------------------------------------

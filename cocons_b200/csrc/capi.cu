@@ -196,7 +196,7 @@ struct cocons_ctx {
   double* dSite = nullptr;
   int* dOrig = nullptr;
   double* dA = nullptr;
-  CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr};
+  CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* dRhs = nullptr;   // n_pad x 2*kMaxRhs
   double* dGram = nullptr;  // Gram + partials + scalars
   // pinned staging
@@ -208,6 +208,7 @@ struct cocons_ctx {
   double nu_fixed = 0, global_range = 1, lim[2] = {0, 0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double ms[4] = {0, 0, 0, 0};
+  double kernel_ms = 0, kernel_flops = 0;  // largest trailing-update launch of the last factorisation
   SiteTable table() const { return SiteTable{dSite, n_pad, dOrig}; }
 };
 
@@ -499,6 +500,16 @@ static int finish_timings(cocons_ctx* c) {
   COCONS_CUDA_TRY(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
   COCONS_CUDA_TRY(cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
   c->ms[0] = a, c->ms[1] = b, c->ms[2] = d, c->ms[3] = a + b + d;
+  c->kernel_ms = 0, c->kernel_flops = 0;
+  const int64_t rest = c->n_pad - 8 * kTile;  // rows/cols right of the first two 512-wide panels
+  if (rest > 0) {
+    float km = 0;
+    if (cudaEventElapsedTime(&km, c->ws.ev_k0, c->ws.ev_k1) == cudaSuccess) {
+      const double tiles = 2.0 * ((double)(rest / kTile) * (rest / kTile + 1) / 2.0);  // 128 x 64 tiles computed
+      c->kernel_ms = km;
+      c->kernel_flops = tiles * 2.0 * 128.0 * 64.0 * 512.0;
+    }
+  }
   return 0;
 }
 
@@ -848,7 +859,7 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
   if (rc) return rc;
   PredBlock blk;
   double *dS = nullptr, *dE = nullptr, *dO = nullptr;
-  CholWorkspace ws2{nullptr, nullptr, nullptr, nullptr, nullptr};
+  CholWorkspace ws2{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   auto cleanup = [&]() { cudaFree(dS), cudaFree(dE), cudaFree(dO), chol_workspace_destroy(&ws2); };
   if (cudaMalloc(&blk.dXp, sizeof(double) * mp * p) != cudaSuccess ||
       cudaMalloc(&blk.dLp, sizeof(double) * mp * 2) != cudaSuccess ||
@@ -917,6 +928,12 @@ int cocons_ctx_get_factor(cocons_ctx* c, double* L, int64_t* perm) {
 int cocons_ctx_timings(cocons_ctx* c, double* ms4) {
   if (!c || !ms4) return COCONS_ERR_ARG;
   for (int i = 0; i < 4; ++i) ms4[i] = c->ms[i];
+  return 0;
+}
+
+int cocons_ctx_kernel_timing(cocons_ctx* c, double* ms, double* flops) {
+  if (!c || !ms || !flops) return COCONS_ERR_ARG;
+  *ms = c->kernel_ms, *flops = c->kernel_flops;
   return 0;
 }
 

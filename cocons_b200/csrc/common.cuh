@@ -80,6 +80,7 @@ struct CholWorkspace {
   int* info;                  // device flag: 0 ok, k > 0 first non-positive pivot (1-based)
   cudaStream_t panel_stream;  // high-priority side stream for the look-ahead panel
   cudaEvent_t ev_a, ev_p;
+  cudaEvent_t ev_k0, ev_k1;  // bracket the largest trailing-update launch (roofline measurement)
 };
 int chol_workspace_create(int64_t n_pad, CholWorkspace* ws);
 void chol_workspace_destroy(CholWorkspace* ws);

@@ -141,7 +141,7 @@ struct cocons_dist {
   double* slab = nullptr;  // n_pad x (local columns), ld = n_pad
   double* tmp = nullptr;   // kPanelW x 2*kDistMaxRhs scratch for the diagonal-block solve
   double* dScal = nullptr;
-  CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr};
+  CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int mode = 0;
   double nu_fixed = 0, global_range = 1, lim[2] = {0, 0};
   int64_t width(int64_t K) const { return std::min<int64_t>(kPanelW, n_pad - K * kPanelW); }

@@ -139,6 +139,10 @@ int cocons_ctx_get_factor(cocons_ctx* ctx, double* L, int64_t* perm);
  * the context's stream): [0] site+assembly [1] factorisation [2] solves+reductions [3] total */
 int cocons_ctx_timings(cocons_ctx* ctx, double* ms4);
 
+/* duration (ms, CUDA events inside the evaluation) and flop count of the LARGEST trailing-update launch of
+ * the last factorisation - the dominant kernel's own roofline point (bench.py) */
+int cocons_ctx_kernel_timing(cocons_ctx* ctx, double* ms, double* flops);
+
 /* ---- one-shot objective, host buffers in, scalars out ------------------
  * What the R closure GetNeg2loglikelihood{,Profile,REML} binds to: uploads
  * locs / X / z / x_betas every call (they arrive as R objects every call),
