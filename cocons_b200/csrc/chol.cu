@@ -483,18 +483,20 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
 }
 
 // ---------------------------------------------------------------------------
-// Diagonal tile: Cholesky of a 128 x 128 tile and its explicit inverse W = L^-1
-// (which turns the panel solve and the later forward substitutions into plain
-// products), with the whole tile held in REGISTERS.
+// Diagonal tile: Cholesky of a 128 x 128 tile and, in the SAME sweep, its explicit inverse
+// W = L^-1 (which turns the panel solve and the later forward substitutions into plain
+// products), with both matrices held in REGISTERS.
 //
-// 256 threads as a 16 x 16 grid, thread (tx, ty) = (tid >> 4, tid & 15) owns the
-// 2-D cyclic set (i = ty + 16 a, j = tx + 16 b), a >= b.  The 16 threads that
-// share a column index form a half-warp, so the pivot is broadcast by shuffle;
-// the scaled column travels through a double-buffered 1 KB shared vector and
-// every thread applies the rank-1 update to its own registers: one block
-// barrier per column, no shared-memory matrix.  The inverse is built row by
-// row the same way (row of L through shared memory, partial dot products per
-// thread, half-warp shuffle reduction).
+// 256 threads as a 16 x 16 grid, thread (tx, ty) = (tid >> 4, tid & 15) owns the 2-D cyclic set
+// (i = ty + 16 a, j = tx + 16 b), a >= b, of L and of W.  Step k:
+//   * the half-warp that owns column k gets the pivot by shuffle, scales the column by
+//     rsqrt(pivot) and publishes it in a double-buffered 1 KB shared vector;
+//   * the 16 threads that own row k of W publish that row (still unscaled) the same way;
+//   * ONE block barrier; then every thread applies, to its own registers,
+//       L[i][j] -= L[i][k] L[j][k]                       (right-looking Cholesky)
+//       W[i][c] -= L[i][k] / L[k][k] * W~[k][c]           (forward elimination of the identity)
+//     and the owners of row k scale it by 1 / L[k][k].
+// 128 barriers in all, no shared-memory matrix, no cross-thread reductions.
 // ---------------------------------------------------------------------------
 constexpr int PT = kTile;
 
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(256, 1)
                       int first_index) {
   __shared__ double colbuf[2][PT];
   __shared__ double rowbuf[2][PT];
+  __shared__ double rdiag[2];
   __shared__ int fail;
   const int tid = threadIdx.x, lane = tid & 31;
   const int tx = tid >> 4, ty = tid & 15;
@@ -521,12 +524,15 @@ __global__ void __launch_bounds__(256, 1)
   bool stop = false;
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll 1
     for (int kx = 0; kx < 16 && !stop; ++kx) {
       const int k = kb * 16 + kx;
       double* cb = colbuf[k & 1];
-      if (tx == kx) {  // the half-warp that owns column k
+      double* rb = rowbuf[k & 1];
+      if (tx == kx) {  // the half-warp that owns column k of L
         const double d = __shfl_sync(hmask, r[kb][kb], (lane & 16) | kx);
-        const double piv = sqrt(d), rinv = 1.0 / piv;
+        // one reciprocal square root on the critical path (dpotf2 scales by 1/sqrt(d) as well)
+        const double rinv = rsqrt(d), piv = d * rinv;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const int i = ty + 16 * a;
@@ -539,21 +545,48 @@ __global__ void __launch_bounds__(256, 1)
             cb[i] = 0.0;
           }
         }
-        if (!(d > 0.0) && ty == kx) {  // non-positive or NaN pivot: dpotrf's info = k+1
-          fail = 1;
-          atomicCAS(info, 0, first_index + k + 1);
+        if (ty == kx) {
+          rdiag[k & 1] = rinv;
+          if (!(d > 0.0)) {  // non-positive or NaN pivot: dpotrf's info = k+1
+            fail = 1;
+            atomicCAS(info, 0, first_index + k + 1);
+          }
+        }
+      }
+      if (ty == kx) {  // the 16 threads that own row k of W: publish it unscaled, 1 on the diagonal
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int c = tx + 16 * b;
+          rb[c] = (b <= kb && c < k) ? w[kb][b] : ((c == k) ? 1.0 : 0.0);
         }
       }
       __syncthreads();
       stop = (fail != 0);
       if (!stop) {
+        const double rinv = rdiag[k & 1];
+        double li[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) li[a] = (a >= kb) ? cb[ty + 16 * a] : 0.0;  // zero for i <= k
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
           if (b >= kb) {
             const double lj = cb[tx + 16 * b];  // zero for j <= k: finished columns stay untouched
 #pragma unroll
             for (int a = 0; a < 8; ++a)
-              if (a >= b) r[a][b] = fma(-cb[ty + 16 * a], lj, r[a][b]);
+              if (a >= b) r[a][b] = fma(-li[a], lj, r[a][b]);
+          }
+          if (b <= kb) {
+            const double wk = rb[tx + 16 * b];  // row k of W before its scaling, zero right of column k
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              if (a >= kb && a >= b) w[a][b] = fma(-(li[a] * rinv), wk, w[a][b]);
+          }
+        }
+        if (ty == kx) {  // row k of W is final once scaled
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const int c = tx + 16 * b;
+            if (b <= kb) w[kb][b] = (c < k) ? w[kb][b] * rinv : ((c == k) ? rinv : w[kb][b]);
           }
         }
       }
@@ -561,55 +594,16 @@ __global__ void __launch_bounds__(256, 1)
   }
   if (stop) return;
 
-  // L back to the matrix; the strict upper part of the tile is zeroed
+  // L back to the matrix (the strict upper part of the tile is zeroed) and W = L^-1, 128 x 128
+  // column-major, zero above the diagonal
 #pragma unroll
   for (int b = 0; b < 8; ++b)
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int i = ty + 16 * a, j = tx + 16 * b;
-      A[(int64_t)j * ld + i] = (a >= b && i >= j) ? r[a][b] : 0.0;
-    }
-
-  // W = L^-1 by rows: W[r][c] = (delta_rc - sum_{k=c}^{r-1} L[r][k] W[k][c]) / L[r][r]
-#pragma unroll
-  for (int rb = 0; rb < 8; ++rb) {
-    for (int rx = 0; rx < 16; ++rx) {
-      const int row = rb * 16 + rx;
-      double* rbuf = rowbuf[row & 1];
-      if (ty == rx) {  // the 16 threads holding row `row` of L publish it (zero right of the diagonal)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int j = tx + 16 * b;
-          rbuf[j] = (b <= rb && j <= row) ? r[rb][b] : 0.0;
-        }
-      }
-      __syncthreads();
-      const double dinv = 1.0 / rbuf[row];
-      double lk[8];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) lk[a] = (a <= rb && ty + 16 * a < row) ? rbuf[ty + 16 * a] : 0.0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b <= rb) {
-          double s = 0.0;
-#pragma unroll
-          for (int a = 0; a < 8; ++a)
-            if (a >= b && a <= rb) s = fma(lk[a], w[a][b], s);
-#pragma unroll
-          for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(hmask, s, off);
-          const int c = tx + 16 * b;
-          if (ty == rx && c <= row) w[rb][b] = (((c == row) ? 1.0 : 0.0) - s) * dinv;
-        }
-      }
-    }
-  }
-  // Winv: 128 x 128 column-major, element (row, col) = W[row][col], zero above the diagonal
-#pragma unroll
-  for (int b = 0; b < 8; ++b)
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int i = ty + 16 * a, j = tx + 16 * b;
-      Winv[j * PT + i] = (a >= b && i >= j) ? w[a][b] : 0.0;
+      const bool low = (a >= b && i >= j);
+      A[(int64_t)j * ld + i] = low ? r[a][b] : 0.0;
+      Winv[j * PT + i] = low ? w[a][b] : 0.0;
     }
 }
 
