@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     cov_rns,
     cov_rns_classic,
     cov_rns_pred,
+    fd_value_and_grad,
     getCovMatrix,
     getDesignMatrix,
     getModelLists,

@@ -405,10 +405,45 @@ def getCovMatrix(coco_object):
     return cov_rns(theta_list, coco_object.locs, x_covs, coco_object.info["smooth.limits"])
 
 
-def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", optim_control=None, device=0):
-    """R/optim.R:65-365, dense branch.  L-BFGS-B (scipy) stands in for optimParallel; the finite-
-    difference objective evaluations all run on the device-resident context instead of forked R
-    workers.  `boundaries` = dict(theta_init, theta_lower, theta_upper)."""
+def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None):
+    """What optimParallel does per L-BFGS-B iteration (R/optim.R:157,256,321; options at
+    R/profile.R:9-16): fn(theta) and its finite-difference neighbours (2p central, or p forward)
+    evaluated as ONE batch of independent points.  With torch.distributed initialised (one process
+    per GPU) the batch is dealt to the ranks by distributed.fan_out(); every rank gets every value,
+    so all ranks take the same optimiser step."""
+    from .distributed import fan_out
+    theta = np.asarray(theta, dtype=np.float64)
+    p = theta.shape[0]
+    pts, spans = [theta.copy()], []
+    for i in range(p):
+        up, dn = theta.copy(), theta.copy()
+        up[i] = min(theta[i] + ndeps, upper[i])
+        dn[i] = theta[i] if forward else max(theta[i] - ndeps, lower[i])
+        if up[i] == dn[i]:  # pinned at a degenerate bound
+            dn[i] = max(theta[i] - ndeps, lower[i])
+        pts.append(up)
+        if not forward:
+            pts.append(dn)
+        spans.append((up[i], dn[i]))
+    vals = fan_out(pts, fn, group=group)
+    f0 = vals[0]
+    grad = np.empty(p)
+    for i in range(p):
+        up_i, dn_i = spans[i]
+        if forward:
+            grad[i] = (vals[1 + i] - f0) / (up_i - dn_i) if up_i != dn_i else 0.0
+        else:
+            grad[i] = (vals[1 + 2 * i] - vals[2 + 2 * i]) / (up_i - dn_i) if up_i != dn_i else 0.0
+    return f0, grad
+
+
+def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", optim_control=None, device=0,
+              forward=False):
+    """R/optim.R:65-365, dense branch.  L-BFGS-B (scipy) stands in for optimParallel's optimiser; its
+    gradient is the same batched finite-difference scheme (fd_value_and_grad), whose independent
+    objective evaluations run on the device-resident context of each rank - across all GPUs when
+    launched with one process per GPU - instead of on forked R workers.
+    `boundaries` = dict(theta_init, theta_lower, theta_upper)."""
     from scipy.optimize import minimize
 
     dm = getDesignMatrix(coco_object.model_list, coco_object.data)
@@ -420,8 +455,9 @@ def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", opt
     if optim_type == "ml":
         lam = (coco_object.info["lambda.Sigma"], coco_object.info["lambda.betas"], coco_object.info["lambda.reg"])
     optim_type = optim_type.lower()
-    ctrl = {"maxiter": 500, "ftol": 1e-8, "eps": np.finfo(float).eps ** 0.25, "maxcor": 100}
+    ctrl = {"maxiter": 500, "ftol": 1e-8, "maxcor": 100}  # R/profile.R:9-16 (factr, maxit, lmm)
     ctrl.update(optim_control or {})
+    ndeps = ctrl.pop("ndeps", np.finfo(float).eps ** 0.25)
     init = np.asarray(boundaries["theta_init"], dtype=np.float64)
     lower = np.asarray(boundaries["theta_lower"], dtype=np.float64)
     upper = np.asarray(boundaries["theta_upper"], dtype=np.float64)
@@ -446,7 +482,8 @@ def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", opt
         def fn(theta):
             return _objective(kind, theta, par_pos, None, None, lim, None, n, lam, safe, ctx=ctx)
 
-        res = minimize(fn, init, method="L-BFGS-B", bounds=list(zip(lower, upper)), options=ctrl)
+        res = minimize(lambda th: fd_value_and_grad(fn, th, lower, upper, ndeps, forward=forward), init, jac=True,
+                       method="L-BFGS-B", bounds=list(zip(lower, upper)), options=ctrl)
         par = res.x
         if optim_type in ("pml", "reml"):  # R/optim.R:326-345
             theta_list = getModelLists(par, par_pos, "diff")

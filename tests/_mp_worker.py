@@ -145,6 +145,12 @@ def main():
     # regime 1: fan-out of independent evaluations
     pts = [0.1 * k for k in range(7)]
     res["fan"] = fan_out(pts, lambda x: x * x + rank * 0.0)
+    # the optimiser's batched finite-difference gradient over the same fan-out
+    from cocons_b200.api import fd_value_and_grad
+    quad = lambda th: float(np.sum((th - np.array([0.5, -1.0, 2.0])) ** 2) + 3.0)  # noqa: E731
+    f0, g = fd_value_and_grad(quad, np.array([0.0, 0.0, 3.0]), np.array([-5.0, -5.0, -5.0]), np.array([5.0, 5.0, 3.0]),
+                              1e-4)
+    res["fd"] = [f0] + list(g)
     if rank == 0:
         S = cov.cov_rns(tl, locs, X, lim)
         R = rmirror.r_chol(S)

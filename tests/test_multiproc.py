@@ -26,3 +26,7 @@ def test_world_size_two_matches_single_process_reference():
     assert np.allclose(res["profile"], res["profile_ref"], rtol=1e-9, atol=0)
     assert res["notpd"] == "NotPositiveDefinite"
     assert np.allclose(res["fan"], [(0.1 * k) ** 2 for k in range(7)])
+    # f = |th - c|^2 + 3 at th = (0, 0, 3), c = (.5, -1, 2); third coordinate sits on its upper bound
+    assert abs(res["fd"][0] - (0.25 + 1 + 1 + 3)) < 1e-12
+    assert np.allclose(res["fd"][1:3], [-1.0, 2.0], atol=1e-6)
+    assert abs(res["fd"][3] - 2.0) < 2e-4  # one-sided at the bound
