@@ -405,7 +405,7 @@ def getCovMatrix(coco_object):
     return cov_rns(theta_list, coco_object.locs, x_covs, coco_object.info["smooth.limits"])
 
 
-def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None):
+def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None, batch=None):
     """What optimParallel does per L-BFGS-B iteration (R/optim.R:157,256,321; options at
     R/profile.R:9-16): fn(theta) and its finite-difference neighbours (2p central, or p forward)
     evaluated as ONE batch of independent points.  With torch.distributed initialised (one process
@@ -425,7 +425,17 @@ def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None)
         if not forward:
             pts.append(dn)
         spans.append((up[i], dn[i]))
-    vals = fan_out(pts, fn, group=group)
+    if batch is not None:  # several evaluations in flight on this GPU (DenseLikelihoodPool.map)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            mine = batch(pts[rank::world])
+            it = iter(mine)
+            vals = fan_out(pts, lambda _pt: next(it), group=group)
+        else:
+            vals = batch(pts)
+    else:
+        vals = fan_out(pts, fn, group=group)
     f0 = vals[0]
     grad = np.empty(p)
     for i in range(p):
@@ -437,7 +447,7 @@ def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None)
     return f0, grad
 
 
-def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", optim_control=None, device=0,
+def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml", optim_control=None, device=0,
               forward=False):
     """R/optim.R:65-365, dense branch.  L-BFGS-B (scipy) stands in for optimParallel's optimiser; its
     gradient is the same batched finite-difference scheme (fd_value_and_grad), whose independent
@@ -474,16 +484,25 @@ def cocoOptim(coco_object, boundaries, ncores=1, safe=True, optim_type="ml", opt
         par_pos["mean"] = np.zeros_like(dm["par.pos"]["mean"])
         if optim_type == "reml":
             z = reml_contrasts(mod_DM, z)
-    with DenseLikelihood(coco_object.locs, mod_DM, z, device=device) as ctx:
+    # `ncores` keeps its meaning of "objective evaluations in flight" (R/optim.R:80-86): here they are
+    # contexts on one GPU; "auto" = as many as fit comfortably, none extra once one evaluation fills the GPU
+    if ncores == "auto":
+        ncores = max(1, min(8, int(4e9 // (8 * n * n))))
+    with DenseLikelihoodPool(coco_object.locs, mod_DM, z, size=int(ncores), device=device) as pool:
+        ctx = pool.ctxs[0]
         if optim_type == "pml":
-            ctx.set_xbetas(x_betas)
+            pool.set_xbetas(x_betas)
         kind = {"ml": _lib.ML, "pml": _lib.PROFILE, "reml": _lib.REML}[optim_type]
 
-        def fn(theta):
-            return _objective(kind, theta, par_pos, None, None, lim, None, n, lam, safe, ctx=ctx)
+        def fn_on(c, theta):
+            return _objective(kind, theta, par_pos, None, None, lim, None, n, lam, safe, ctx=c)
 
-        res = minimize(lambda th: fd_value_and_grad(fn, th, lower, upper, ndeps, forward=forward), init, jac=True,
-                       method="L-BFGS-B", bounds=list(zip(lower, upper)), options=ctrl)
+        def fn(theta):
+            return fn_on(ctx, theta)
+
+        res = minimize(lambda th: fd_value_and_grad(fn, th, lower, upper, ndeps, forward=forward,
+                                                    batch=lambda pts: pool.map(fn_on, pts)),
+                       init, jac=True, method="L-BFGS-B", bounds=list(zip(lower, upper)), options=ctrl)
         par = res.x
         if optim_type in ("pml", "reml"):  # R/optim.R:326-345
             theta_list = getModelLists(par, par_pos, "diff")
@@ -561,3 +580,54 @@ def cocoSim(coco_object, pars=None, n=1, seed=None, standardize=True, type="clas
         ctx.factor(theta_to_fit, coco_object.info["smooth.limits"], type=type)
         draws = ctx.sim(eps)
     return draws + (std_coco @ theta_to_fit["mean"])[:, None]
+
+
+# --------------------------------------------------------------------------
+# several evaluations in flight on ONE GPU
+# --------------------------------------------------------------------------
+class DenseLikelihoodPool:
+    """`size` device-resident contexts over the same data, each with its own streams, driven by host
+    threads (the C ABI releases the GIL).  Below n ~ 10 000 one evaluation is a latency-bound chain of
+    small kernels that leaves most of the 148 SMs idle; running the optimiser's independent
+    finite-difference points (R/optim.R:157,256,321) side by side fills them."""
+
+    def __init__(self, locs, x_covariates, z, size=4, device=0):
+        from concurrent.futures import ThreadPoolExecutor
+        self.ctxs = [DenseLikelihood(locs, x_covariates, z, device=device) for _ in range(int(size))]
+        self.exec = ThreadPoolExecutor(max_workers=len(self.ctxs))
+        self.n, self.p, self.r = self.ctxs[0].n, self.ctxs[0].p, self.ctxs[0].r
+
+    def close(self):
+        self.exec.shutdown(wait=True)
+        for c in self.ctxs:
+            c.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_xbetas(self, xb):
+        for c in self.ctxs:
+            c.set_xbetas(xb)
+
+    def set_z(self, z):
+        for c in self.ctxs:
+            c.set_z(z)
+
+    def map(self, fn, points):
+        """[fn(ctx, point) for point in points], evaluated len(ctxs) at a time."""
+        import queue
+        free = queue.SimpleQueue()
+        for c in self.ctxs:
+            free.put(c)
+
+        def run(pt):
+            c = free.get()
+            try:
+                return fn(c, pt)
+            finally:
+                free.put(c)
+
+        return list(self.exec.map(run, points))
