@@ -4,14 +4,13 @@
 // a multiple of 128 (identity in the padding).
 //
 //   potrf_tile_kernel   K3: 128x128 diagonal tile, factor + explicit inverse
-//   gemm_nt_kernel      K4/K5: C (-)= A B^T on FP64 tensor cores (DMMA.8x8x4 via
+//   gemm_nt_tma_kernel  K4/K5: C (-)= A B^T on FP64 tensor cores (DMMA.8x8x4 via
 //                       mma.sync.m8n8k4.f64), operands streamed global->shared by
-//                       the async copy engine; used for the panel solve
-//                       (X = A inv(L_jj)^T), the in-panel update and the trailing
-//                       SYRK update
+//                       the bulk-copy (TMA) engine onto mbarriers; used for the panel
+//                       solve (X = A inv(L_jj)^T), the in-panel update and the
+//                       trailing SYRK update
 //   chol_factor         two-level driver: 128-wide steps inside 512-wide panels
 #include <algorithm>
-#include <cstdlib>
 
 #include "../../include/cocons_b200.h"
 #include "common.cuh"
@@ -22,7 +21,7 @@ namespace cocons {
 // DMMA NT GEMM.  C[M x N] (-)= A[M x K] * B[N x K]^T, everything column-major,
 // M, N multiples of 128, K a multiple of 16.
 //
-// CTA tile 128(i) x 128(j), 8 warps as 2(i) x 4(j), warp tile 64(i) x 32(j).
+// CTA tile 128(i) x 64(j) (128 x 128 for the panel solve), warp tile 32(i) x 32(j).
 // The mma's M dimension runs over matrix COLUMNS j and its N dimension over
 // matrix ROWS i, so that the two accumulator registers of a thread are two
 // consecutive rows of one column; with fragment row g of the tile pair
@@ -33,36 +32,25 @@ namespace cocons {
 constexpr int GBM = 128, GBK = 16, GSTAGES = 4;
 constexpr int GLDA = GBM + 4;  // padded leading dimension of a shared k-row (== 4 mod 16: conflict-free LDS.128)
 
-template <int BN, int NU = 4>
+template <int BN, int NU = 2>
 struct GemmCfg {
-  static constexpr int kWarpI = 16 * NU;             // warp tile is (16 NU)(i) x 32(j): NU = 4 -> 64, NU = 2 -> 32
+  static constexpr int kWarpI = 16 * NU;             // warp tile is (16 NU)(i) x 32(j); NU = 2: 32 x 32
   static constexpr int kWarpsI = GBM / kWarpI;
   static constexpr int kWarpsJ = BN / 32;
   static constexpr int kThreads = kWarpsI * kWarpsJ * 32;
   static constexpr int kLdb = BN + 4;
   static constexpr int kStageDoubles = GBK * (GLDA + kLdb);
   static constexpr int kSmemBytes = GSTAGES * kStageDoubles * (int)sizeof(double);
-  // BN = 64: 128 threads x 192 registers and ~100 KB of shared memory, so TWO CTAs share an SM and
-  // one runs its main loop while the other is in its prologue / read-modify-write epilogue
+  // BN = 64: 8 warps of 32 x 32 (116 registers) and ~100 KB of shared memory per CTA, so TWO CTAs share an
+  // SM (4 warps per scheduler): one runs its main loop while the other is in its prologue or its
+  // read-modify-write epilogue.  BN = 128 (in-place panel solve): 16 warps, one CTA per SM.
   static constexpr int kMinBlocks = (BN == 64) ? 2 : 1;
 };
-// BN = 64, NU = 2: 8 warps of 32 x 32 per CTA (<= 128 registers), two CTAs per SM = 4 warps per
-// scheduler, so that two warps are left to interleave DMMAs while others wait on LDS / barriers.
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(d0), "+d"(d1)
       : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // Tile rasterisation.  Tiles are visited band by band (16 tile rows = 2048 matrix rows per band),
@@ -128,150 +116,15 @@ __device__ __forceinline__ void tile_decode(int64_t t, int ni, int njc, int lowe
   }
 }
 
-template <int BN, int NU, int ASSIGN>
-__global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kMinBlocks)
-    gemm_nt_kernel(int ni, int nj, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                   int64_t ldc, int lower_only, int64_t ntiles, int dbg) {
-  // Persistent: CTA b walks tiles b, b + gridDim.x, ... and keeps ONE cp.async pipeline running across
-  // tile boundaries, so the first stages of the next tile are already in flight while the
-  // read-modify-write epilogue of the current one runs.
-  using Cfg = GemmCfg<BN, NU>;
-  extern __shared__ __align__(16) double smem[];
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, c4 = lane & 3;
-  const int iw = (warp % Cfg::kWarpsI) * Cfg::kWarpI, jw = (warp / Cfg::kWarpsI) * 32;
-
-  auto decode = [&](int64_t t, int& bi, int& bj) { tile_decode<GBM / BN>(t, ni, nj, lower_only, bi, bj); };
-  auto As = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles; };
-  auto Bs = [&](int s) { return smem + (size_t)s * Cfg::kStageDoubles + GBK * GLDA; };
-
-  const int64_t nkb = K / GBK;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
-  const int64_t my_tiles = (ntiles > first) ? (ntiles - first + stride - 1) / stride : 0;
-  const int64_t total = my_tiles * nkb;
-
-  // loader state: which (tile, k-block) the next cp.async stage belongs to
-  int64_t ld_it = 0, ld_tile = 0, ld_kb = 0;
-  const double* ld_A = A;
-  const double* ld_B = B;
-  auto issue_load = [&]() {
-    if (ld_it < total) {
-      if (ld_kb == 0) {
-        int bi, bj;
-        decode(first + ld_tile * stride, bi, bj);
-        ld_A = A + (int64_t)bi * GBM;
-        ld_B = B + (int64_t)bj * BN;
-      }
-      double* as = As((int)(ld_it % GSTAGES));
-      double* bs = Bs((int)(ld_it % GSTAGES));
-#pragma unroll
-      for (int c = tid; c < GBK * (GBM / 2); c += Cfg::kThreads) {
-        const int k = c / (GBM / 2), i2 = c % (GBM / 2);
-        cp_async16(as + k * GLDA + 2 * i2, ld_A + (ld_kb * GBK + k) * lda + 2 * i2);
-      }
-#pragma unroll
-      for (int c = tid; c < GBK * (BN / 2); c += Cfg::kThreads) {
-        const int k = c / (BN / 2), j2 = c % (BN / 2);
-        cp_async16(bs + k * Cfg::kLdb + 2 * j2, ld_B + (ld_kb * GBK + k) * ldb + 2 * j2);
-      }
-      ++ld_it;
-      if (++ld_kb == nkb) ld_kb = 0, ++ld_tile;
-    }
-    cp_async_commit();
-  };
-
-  double acc[4][2 * NU][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 2 * NU; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
-#pragma unroll
-  for (int s = 0; s < GSTAGES - 1; ++s) issue_load();
-
-  int64_t kb = 0, tile = 0;
-  double* Cg = nullptr;
-  for (int64_t it = 0; it < total; ++it) {
-    if (kb == 0) {
-      int bi, bj;
-      decode(first + tile * stride, bi, bj);
-      Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
-      if (!ASSIGN) {  // pull the C tile towards L2 while the main loop runs
-        for (int l = tid; l < BN * 8; l += Cfg::kThreads)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + (int64_t)(l >> 3) * ldc + (l & 7) * 16));
-      }
-    }
-    cp_async_wait<GSTAGES - 2>();
-    if (!(dbg & 4)) __syncthreads();
-    if (!(dbg & 2)) issue_load(); else cp_async_commit();
-    const double* as = As((int)(it % GSTAGES)) + iw + 2 * g;
-    const double* bs = Bs((int)(it % GSTAGES)) + jw + 2 * g;
-#pragma unroll
-    for (int kk = 0; kk < GBK / 4; ++kk) {
-      const int k = kk * 4 + c4;
-      double fi[2 * NU], fj[4];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const double2 v = *reinterpret_cast<const double2*>(as + k * GLDA + 16 * u);
-        fi[2 * u] = v.x;
-        fi[2 * u + 1] = v.y;
-      }
-#pragma unroll
-      for (int v2 = 0; v2 < 2; ++v2) {
-        const double2 v = *reinterpret_cast<const double2*>(bs + k * Cfg::kLdb + 16 * v2);
-        fj[2 * v2] = v.x;
-        fj[2 * v2 + 1] = v.y;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2 * NU; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
-    }
-    if (++kb == nkb && (dbg & 1)) { kb = 0; ++tile; if (it + 1 == total) C[tid] = acc[0][0][0] + acc[3][1][1]; }
-    else if (kb == nkb) {
-      // epilogue: a thread owns rows r0..r0+3 of column j for every (a, u)
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int j = jw + 16 * (a >> 1) + 2 * g + (a & 1);
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-          const int r0 = iw + 16 * u + 4 * c4;
-          double2* p = reinterpret_cast<double2*>(Cg + (int64_t)j * ldc + r0);
-          double2 lo, hi;
-          if (ASSIGN) {
-            lo.x = acc[a][2 * u][0];
-            lo.y = acc[a][2 * u + 1][0];
-            hi.x = acc[a][2 * u][1];
-            hi.y = acc[a][2 * u + 1][1];
-          } else {
-            lo = p[0];
-            hi = p[1];
-            lo.x -= acc[a][2 * u][0];
-            lo.y -= acc[a][2 * u + 1][0];
-            hi.x -= acc[a][2 * u][1];
-            hi.y -= acc[a][2 * u + 1][1];
-          }
-          p[0] = lo;
-          p[1] = hi;
-          acc[a][2 * u][0] = acc[a][2 * u + 1][0] = acc[a][2 * u][1] = acc[a][2 * u + 1][1] = 0.0;
-        }
-      }
-      kb = 0;
-      ++tile;
-    }
-  }
-  cp_async_wait<0>();
-}
-
 // ---------------------------------------------------------------------------
-// Same tile computation, operands fed by the bulk-copy (TMA) engine instead of per-thread LDGSTS.
-// One elected lane issues, per stage, 32 `cp.async.bulk` row copies (16 k-rows of A and of B, each a
-// contiguous 1 KB / BN*8 B segment of a matrix column) straight into the padded shared rows; the
-// bytes land on an mbarrier (`complete_tx`).  Consumers wait on that barrier and hand the slot back
-// through an `empty` mbarrier - no __syncthreads, no cp.async.wait_group, no per-thread address
+// Operand feed: the bulk-copy (TMA) engine.  One elected lane issues, per stage, 32 `cp.async.bulk` row
+// copies (16 k-rows of A and of B, each a contiguous 1 KB / BN*8 B segment of a matrix column) straight
+// into the padded shared rows; the bytes land on an mbarrier (`complete_tx`).  Consumers wait on that
+// barrier and hand the slot back through an `empty` mbarrier - no __syncthreads, no per-thread address
 // arithmetic in the MMA warps.  The producer role rotates over the warps (stage s is issued by warp
-// s mod nwarps) so that no warp is permanently behind.  One tile per CTA, two CTAs per SM.
+// s mod nwarps) so that no warp is permanently behind.  One tile per CTA.
+// (An earlier version fed the operands with per-thread cp.async/LDGSTS and a block barrier per stage:
+// 31.9 TFLOP/s against 35.3 for this one; the ablation is in profiles/r01_gemm_tma_v3_ncu.md.)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -424,61 +277,34 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
   }
 }
 
-// mode 0: C -= A B^T on 128 x 64 tiles (two CTAs per SM); mode 1: C = A B^T on 128 x 128 tiles -
-// the in-place panel solve needs one CTA to own the whole 128-column block it overwrites.
+// mode 0: C -= A B^T on 128 x 64 tiles, 8 warps, two CTAs per SM; mode 1: C = A B^T on 128 x 128 tiles,
+// 16 warps, one CTA per SM - the in-place panel solve needs one CTA to own the whole 128-column block
+// it overwrites (every bulk copy of its A rows has landed before its first store).
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return;
   static bool attr_done[16] = {};
-  static int variant = -1, dbg = 0;
-  if (variant < 0) {
-    const char* d = getenv("COCONS_GEMM_DEBUG");  // timing experiments only (results are wrong when set)
-    dbg = d ? atoi(d) : 0;
-    const char* e = getenv("COCONS_GEMM_VARIANT");  // tuning knob: 0/1 = LDGSTS feed (4 warps of 64x32 / 8 warps of 32x32), 2/3 = bulk-copy (TMA) feed, same shapes; default 3
-    variant = e ? atoi(e) : 3;
-  }
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
-    cudaFuncSetAttribute(gemm_nt_kernel<64, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64, 4>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_nt_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64, 2>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_nt_kernel<128, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<128, 4>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64, 4>::kSmemBytes + 64);
     cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          GemmCfg<64, 2>::kSmemBytes + 64);
+    cudaFuncSetAttribute(gemm_nt_tma_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<128, 2>::kSmemBytes + 64);
     attr_done[dev] = true;
   }
-  static int num_sms[16] = {};
-  if (dev < 16 && num_sms[dev] == 0) cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
-  const int sms = (dev < 16 && num_sms[dev] > 0) ? num_sms[dev] : 148;
   const int ni = (int)(M / GBM);
   note_launch();
   if (mode == 1) {
     const int nj = (int)(N / 128);
     const int64_t tiles = total_tiles<1>(ni, nj, lower_only);
-    const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
-    gemm_nt_kernel<128, 4, 1><<<grid, GemmCfg<128, 4>::kThreads, GemmCfg<128, 4>::kSmemBytes, st>>>(
-        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
+    gemm_nt_tma_kernel<128, 2, 1><<<(unsigned)tiles, GemmCfg<128, 2>::kThreads, GemmCfg<128, 2>::kSmemBytes + 64, st>>>(
+        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
   } else {
     const int nj = (int)(N / 64);
     const int64_t tiles = total_tiles<2>(ni, nj, lower_only);
-    const unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)sms);
-    if (variant == 2)
-      gemm_nt_tma_kernel<64, 4, 0><<<(unsigned)tiles, GemmCfg<64, 4>::kThreads, GemmCfg<64, 4>::kSmemBytes + 64, st>>>(
-          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
-    else if (variant == 3)
-      gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64, st>>>(
-          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
-    else if (variant == 1)
-      gemm_nt_kernel<64, 2, 0><<<grid, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes, st>>>(
-          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
-    else
-      gemm_nt_kernel<64, 4, 0><<<grid, GemmCfg<64, 4>::kThreads, GemmCfg<64, 4>::kSmemBytes, st>>>(
-          ni, nj, K, A, lda, B, ldb, C, ldc, lower_only, tiles, dbg);
+    gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64, st>>>(
+        ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
   }
 }
 
