@@ -6,8 +6,12 @@
 //   crossprod(.)                                   :148, :157, :214, :276, :285
 // All of them are HBM-bound: the factor is streamed once per block of
 // right-hand sides (4 n^2 bytes).
+#include <cooperative_groups.h>
+
 #include "../../include/cocons_b200.h"
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cocons {
 
@@ -32,76 +36,98 @@ void launch_logdet(const double* L, int64_t n, int64_t ld, double* out, cudaStre
 }
 
 // ---------------------------------------------------------------------------
-// One step J of the blocked forward substitution  L Y = B  (B overwritten by
-// partially updated right-hand sides, Y a separate buffer):
-//     y_J = inv(L_JJ) b_J ;   b_I -= L_IJ y_J  for every tile row I > J.
-// CTA 0 writes y_J; every CTA recomputes y_J in shared memory (a 128 x 128
-// product out of L2) instead of waiting for another CTA, then updates its own
-// 128 rows.  NR right-hand sides are carried in registers per pass.
+// Blocked forward substitution  L Y = B  for NR right-hand sides in ONE cooperative launch:
+//   for every tile J:   y_J = inv(L_JJ) b_J ;   b_I -= L_IJ y_J  for every tile row I > J ;  grid sync.
+// Every CTA recomputes y_J in shared memory (a 128 x 128 product out of L2) instead of waiting for a
+// broadcast, then updates the tile rows it owns (I = J+1+blockIdx.x, stride gridDim.x); CTA 0 stores y_J.
+// The n/128 dependent steps cost one grid barrier each instead of one kernel launch each.
 // ---------------------------------------------------------------------------
 template <int NR>
-__global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, int64_t ld,
-                                                       const double* __restrict__ Winv, double* __restrict__ B,
-                                                       double* __restrict__ Y, int64_t ldb, int64_t J, int nr) {
+__global__ void __launch_bounds__(256) fwd_solve_coop_kernel(const double* __restrict__ L, int64_t ld,
+                                                             const double* __restrict__ Winv, double* B,
+                                                             double* __restrict__ Y, int64_t ldb, int64_t nt, int nr) {
+  cg::grid_group grid = cg::this_grid();
   __shared__ double bj[NR][kTile];
   __shared__ double yj[NR][kTile];
   __shared__ double part[NR][256];
   const int tid = threadIdx.x;
-  const int64_t j0 = J * kTile;
-  for (int idx = tid; idx < NR * kTile; idx += 256) {
-    const int c = idx / kTile, k = idx % kTile;
-    bj[c][k] = (c < nr) ? B[(int64_t)c * ldb + j0 + k] : 0.0;
-  }
-  __syncthreads();
-  // y = W b: thread (row = tid & 127, half = tid >> 7) sums half of the k range
-  {
-    const int row = tid & (kTile - 1), h = tid >> 7;
-    double acc[NR];
-#pragma unroll
-    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
-    const int kbeg = h ? (row + 2) / 2 : 0, kend = h ? row + 1 : (row + 2) / 2;
-    for (int k = kbeg; k < kend; ++k) {
-      const double w = Winv[(int64_t)k * kTile + row];
-#pragma unroll
-      for (int c = 0; c < NR; ++c) acc[c] = fma(w, bj[c][k], acc[c]);
+  const int row = tid & (kTile - 1), h = tid >> 7;
+  for (int64_t J = 0; J < nt; ++J) {
+    const int64_t j0 = J * kTile;
+    const double* W = Winv + J * (int64_t)kTile * kTile;
+    for (int idx = tid; idx < NR * kTile; idx += 256) {
+      const int c = idx / kTile, k = idx % kTile;
+      bj[c][k] = (c < nr) ? __ldcg(B + (int64_t)c * ldb + j0 + k) : 0.0;  // written by other CTAs: bypass L1
     }
+    __syncthreads();
+    {  // y = W b: thread (row, half) sums half of the k range of its row
+      double acc[NR];
 #pragma unroll
-    for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
-  }
-  __syncthreads();
-  if (tid < kTile) {
+      for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+      // W is stored with explicit zeros above the diagonal: fixed trip count, 16 loads in flight
+      const double* Wp = W + (int64_t)h * (kTile / 2) * kTile + row;
+#pragma unroll 16
+      for (int k = 0; k < kTile / 2; ++k) {
+        const double w = __ldg(Wp + (int64_t)k * kTile);
 #pragma unroll
-    for (int c = 0; c < NR; ++c) {
-      const double y = part[c][tid] + part[c][tid + kTile];
-      yj[c][tid] = y;
-      if (blockIdx.x == 0 && c < nr) Y[(int64_t)c * ldb + j0 + tid] = y;
+        for (int c = 0; c < NR; ++c) acc[c] = fma(w, bj[c][h * (kTile / 2) + k], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
     }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) return;
-  // rows of tile I = J + blockIdx.x: b_I -= L_IJ y_J
-  const int64_t i0 = (J + blockIdx.x) * kTile;
-  {
-    const int row = tid & (kTile - 1), h = tid >> 7;
-    double acc[NR];
+    __syncthreads();
+    if (tid < kTile) {
 #pragma unroll
-    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
-    const double* Lp = L + (j0 + (int64_t)h * (kTile / 2)) * ld + i0 + row;
-#pragma unroll 4
-    for (int k = 0; k < kTile / 2; ++k) {
-      const double l = Lp[(int64_t)k * ld];
-#pragma unroll
-      for (int c = 0; c < NR; ++c) acc[c] = fma(l, yj[c][h * (kTile / 2) + k], acc[c]);
+      for (int c = 0; c < NR; ++c) {
+        const double y = part[c][tid] + part[c][tid + kTile];
+        yj[c][tid] = y;
+        if (blockIdx.x == 0 && c < nr) Y[(int64_t)c * ldb + j0 + tid] = y;
+      }
     }
+    __syncthreads();
+    for (int64_t I = J + 1 + blockIdx.x; I < nt; I += gridDim.x) {  // b_I -= L_IJ y_J
+      const int64_t i0 = I * kTile;
+      double acc[NR];
 #pragma unroll
-    for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
-  }
-  __syncthreads();
-  if (tid < kTile) {
+      for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+      const double* Lp = L + (j0 + (int64_t)h * (kTile / 2)) * ld + i0 + row;
+#pragma unroll 16
+      for (int k = 0; k < kTile / 2; ++k) {
+        const double l = __ldg(Lp + (int64_t)k * ld);
 #pragma unroll
-    for (int c = 0; c < NR; ++c)
-      if (c < nr) B[(int64_t)c * ldb + i0 + tid] -= part[c][tid] + part[c][tid + kTile];
+        for (int c = 0; c < NR; ++c) acc[c] = fma(l, yj[c][h * (kTile / 2) + k], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
+      __syncthreads();
+      if (tid < kTile) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c)
+          if (c < nr) B[(int64_t)c * ldb + i0 + tid] -= part[c][tid] + part[c][tid + kTile];
+      }
+      __syncthreads();
+    }
+    grid.sync();
   }
+}
+
+template <int NR>
+static void launch_fwd_coop(const double* L, int64_t ld, const double* winv, double* B, double* Y, int64_t ldb,
+                            int64_t nt, int nr, cudaStream_t st) {
+  static int max_blocks[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && max_blocks[dev] == 0) {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_solve_coop_kernel<NR>, 256, 0);
+    max_blocks[dev] = sms * (per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm));
+  }
+  int grid = (dev < 16) ? max_blocks[dev] : 148;
+  if (grid > nt) grid = (int)(nt > 0 ? nt : 1);
+  void* args[] = {(void*)&L, (void*)&ld, (void*)&winv, (void*)&B, (void*)&Y, (void*)&ldb, (void*)&nt, (void*)&nr};
+  note_launch();
+  cudaLaunchCooperativeKernel((void*)fwd_solve_coop_kernel<NR>, dim3(grid), dim3(256), args, 0, st);
 }
 
 // L (n_pad x n_pad, lower) Y = B for nrhs columns; on return B holds Y.
@@ -115,19 +141,14 @@ void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* win
     const int nr = (nrhs - c0 < 8) ? nrhs - c0 : 8;
     double* Bc = B + (int64_t)c0 * ldb;
     double* Yc = Y + (int64_t)c0 * ldb;
-    for (int64_t J = 0; J < nt; ++J) {
-      const unsigned blocks = (unsigned)(nt - J);
-      const double* W = winv + J * (int64_t)kTile * kTile;
-      note_launch();
-      if (nr == 1)
-        fwd_step_kernel<1><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
-      else if (nr == 2)
-        fwd_step_kernel<2><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
-      else if (nr <= 4)
-        fwd_step_kernel<4><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
-      else
-        fwd_step_kernel<8><<<blocks, 256, 0, st>>>(L, ld, W, Bc, Yc, ldb, J, nr);
-    }
+    if (nr == 1)
+      launch_fwd_coop<1>(L, ld, winv, Bc, Yc, ldb, nt, nr, st);
+    else if (nr == 2)
+      launch_fwd_coop<2>(L, ld, winv, Bc, Yc, ldb, nt, nr, st);
+    else if (nr <= 4)
+      launch_fwd_coop<4>(L, ld, winv, Bc, Yc, ldb, nt, nr, st);
+    else
+      launch_fwd_coop<8>(L, ld, winv, Bc, Yc, ldb, nt, nr, st);
   }
   cudaMemcpyAsync(B, Y, sizeof(double) * (size_t)nrhs * (size_t)ldb, cudaMemcpyDeviceToDevice, st);
 }
