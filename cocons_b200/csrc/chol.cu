@@ -11,6 +11,7 @@
 //                       trailing SYRK update
 //   chol_factor         two-level driver: 128-wide steps inside 512-wide panels
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/cocons_b200.h"
 #include "common.cuh"
@@ -314,24 +315,33 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
 // products), with both matrices held in REGISTERS.
 //
 // 256 threads as a 16 x 16 grid, thread (tx, ty) = (tid >> 4, tid & 15) owns the 2-D cyclic set
-// (i = ty + 16 a, j = tx + 16 b), a >= b, of L and of W.  Step k:
-//   * the half-warp that owns column k gets the pivot by shuffle, scales the column by
-//     rsqrt(pivot) and publishes it in a double-buffered 1 KB shared vector;
-//   * the 16 threads that own row k of W publish that row (still unscaled) the same way;
-//   * ONE block barrier; then every thread applies, to its own registers,
-//       L[i][j] -= L[i][k] L[j][k]                       (right-looking Cholesky)
-//       W[i][c] -= L[i][k] / L[k][k] * W~[k][c]           (forward elimination of the identity)
-//     and the owners of row k scale it by 1 / L[k][k].
-// 128 barriers in all, no shared-memory matrix, no cross-thread reductions.
+// (i = ty + 16 a, j = tx + 16 b), a >= b, of L and of W.  Step k applies, to registers,
+//     L[i][j] -= L[i][k] L[j][k]                        (right-looking Cholesky)
+//     W[i][c] -= L[i][k] / L[k][k] * W~[k][c]            (forward elimination of the identity)
+// after column k of L (scaled by rsqrt(pivot), pivot broadcast by half-warp shuffle) and the still
+// unscaled row k of W have been published in 1 KB shared vectors.
+//
+// The column is the critical path, so it runs one step AHEAD: inside step k every thread first
+// updates only what step k+1 publishes (column k+1 of L, row k+1 of W), the owners publish it and
+// everybody ARRIVES on the mbarrier of step k+1, and only then is the bulk of step k's update done -
+// the next pivot / rsqrt / scale overlaps the other warps' FMAs.  Three buffers and three mbarriers
+// (k mod 3) make that safe: a buffer is rewritten two steps after its last reader started.
 // ---------------------------------------------------------------------------
 constexpr int PT = kTile;
+#ifdef COCONS_POTRF_PROBE
+__device__ long long g_probe[PT * 8];
+#define PROBE(slot, kk, cond) if (cond) g_probe[(kk) * 8 + (slot)] = clock64()
+#else
+#define PROBE(slot, kk, cond)
+#endif
 
 __global__ void __launch_bounds__(256, 1)
     potrf_tile_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int* __restrict__ info,
                       int first_index) {
-  __shared__ double colbuf[2][PT];
-  __shared__ double rowbuf[2][PT];
-  __shared__ double rdiag[2];
+  __shared__ double colbuf[3][PT];
+  __shared__ double rowbuf[3][PT];
+  __shared__ double rdiag[3];
+  __shared__ __align__(8) uint64_t mbar[3];
   __shared__ int fail;
   const int tid = threadIdx.x, lane = tid & 31;
   const int tx = tid >> 4, ty = tid & 15;
@@ -344,58 +354,86 @@ __global__ void __launch_bounds__(256, 1)
       w[a][b] = 0.0;
       r[a][b] = (a >= b) ? A[(int64_t)(tx + 16 * b) * ld + ty + 16 * a] : 0.0;
     }
-  if (tid == 0) fail = 0;
+  if (tid == 0) {
+    fail = 0;
+    for (int m = 0; m < 3; ++m) mbar_init(smem_u32(&mbar[m]), 256);
+  }
   __syncthreads();
 
-  bool stop = false;
+  // publish column `kk` of L (its owners: tx == kk % 16) and row `kk` of W (ty == kk % 16); NB = kk / 16
+  auto publish = [&](auto nb_tag, int kk) {
+    constexpr int NB = decltype(nb_tag)::value;
+    const int qx = kk & 15;
+    double* cb = colbuf[kk % 3];
+    double* rb = rowbuf[kk % 3];
+    if (tx == qx) {
+      PROBE(1, kk, ty == qx);
+      const double d = __shfl_sync(hmask, r[NB][NB], (lane & 16) | qx);
+      PROBE(2, kk, ty == qx);
+      // one reciprocal square root on the critical path (dpotf2 scales by 1/sqrt(d) as well)
+      const double rinv = rsqrt(d), piv = d * rinv;
+      PROBE(3, kk, ty == qx && rinv > 0);
 #pragma unroll
-  for (int kb = 0; kb < 8; ++kb) {
+      for (int a = 0; a < 8; ++a) {  // rows above block NB are never read by the consumers of this column
+        const int i = ty + 16 * a;
+        if (a >= NB) {
+          double v = r[a][NB];
+          v = (i > kk) ? v * rinv : ((i == kk) ? piv : v);
+          r[a][NB] = v;
+          cb[i] = (i > kk) ? v : 0.0;
+        }
+      }
+      if (ty == qx) {
+        rdiag[kk % 3] = rinv;
+        if (!(d > 0.0)) {  // non-positive or NaN pivot: dpotrf's info = k+1
+          fail = 1;
+          atomicCAS(info, 0, first_index + kk + 1);
+        }
+      }
+    }
+    if (ty == qx) {  // row kk of W, unscaled, 1 on the diagonal, 0 right of it (blocks right of NB are
+                     // never read by the consumers of this row)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int c = tx + 16 * b;
+        if (b <= NB) rb[c] = (c < kk) ? w[NB][b] : ((c == kk) ? 1.0 : 0.0);
+      }
+    }
+    PROBE(4, kk, tx == qx && ty == qx);
+    mbar_arrive(smem_u32(&mbar[kk % 3]));
+    PROBE(5, kk, tx == qx && ty == qx);
+  };
+
+  publish(std::integral_constant<int, 0>{}, 0);
+
+  bool stop = false;
+  auto block_steps = [&](auto kb_tag) {  // the 16 steps of block column kb (kb is a compile-time index)
+    constexpr int kb = decltype(kb_tag)::value;
 #pragma unroll 1
     for (int kx = 0; kx < 16 && !stop; ++kx) {
       const int k = kb * 16 + kx;
-      double* cb = colbuf[k & 1];
-      double* rb = rowbuf[k & 1];
-      if (tx == kx) {  // the half-warp that owns column k of L
-        const double d = __shfl_sync(hmask, r[kb][kb], (lane & 16) | kx);
-        // one reciprocal square root on the critical path (dpotf2 scales by 1/sqrt(d) as well)
-        const double rinv = rsqrt(d), piv = d * rinv;
+      mbar_wait(smem_u32(&mbar[k % 3]), (uint32_t)((k / 3) & 1));
+      PROBE(0, k + 1, tx == ((k + 1) & 15) && ty == ((k + 1) & 15));
+      PROBE(6, k, tid == 255);
+      stop = (*(volatile int*)&fail != 0);
+      if (stop) break;
+      const double* cb = colbuf[k % 3];
+      const double* rb = rowbuf[k % 3];
+      const double rinv = rdiag[k % 3];
+      double li[8], lw[8];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const int i = ty + 16 * a;
-          if (a >= kb) {
-            double v = r[a][kb];
-            v = (i > k) ? v * rinv : ((i == k) ? piv : v);
-            r[a][kb] = v;
-            cb[i] = (i > k) ? v : 0.0;
-          } else {
-            cb[i] = 0.0;
-          }
-        }
-        if (ty == kx) {
-          rdiag[k & 1] = rinv;
-          if (!(d > 0.0)) {  // non-positive or NaN pivot: dpotrf's info = k+1
-            fail = 1;
-            atomicCAS(info, 0, first_index + k + 1);
-          }
-        }
+      for (int a = 0; a < 8; ++a) {
+        li[a] = (a >= kb) ? cb[ty + 16 * a] : 0.0;  // zero for i <= k
+        lw[a] = li[a] * rinv;
       }
-      if (ty == kx) {  // the 16 threads that own row k of W: publish it unscaled, 1 on the diagonal
+      // the update of step k, restricted to block column PB of L and block row PB of W (ONLY = true)
+      // or to everything else (ONLY = false)
+      auto update = [&](auto pb_tag, auto only_tag) {
+        constexpr int PB = decltype(pb_tag)::value;
+        constexpr bool ONLY = decltype(only_tag)::value;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          const int c = tx + 16 * b;
-          rb[c] = (b <= kb && c < k) ? w[kb][b] : ((c == k) ? 1.0 : 0.0);
-        }
-      }
-      __syncthreads();
-      stop = (fail != 0);
-      if (!stop) {
-        const double rinv = rdiag[k & 1];
-        double li[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) li[a] = (a >= kb) ? cb[ty + 16 * a] : 0.0;  // zero for i <= k
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (b >= kb) {
+          if (b >= kb && ((b == PB) == ONLY)) {
             const double lj = cb[tx + 16 * b];  // zero for j <= k: finished columns stay untouched
 #pragma unroll
             for (int a = 0; a < 8; ++a)
@@ -405,19 +443,42 @@ __global__ void __launch_bounds__(256, 1)
             const double wk = rb[tx + 16 * b];  // row k of W before its scaling, zero right of column k
 #pragma unroll
             for (int a = 0; a < 8; ++a)
-              if (a >= kb && a >= b) w[a][b] = fma(-(li[a] * rinv), wk, w[a][b]);
+              if (a >= kb && a >= b && ((a == PB) == ONLY)) w[a][b] = fma(-lw[a], wk, w[a][b]);
           }
         }
-        if (ty == kx) {  // row k of W is final once scaled
+      };
+      if (k + 1 < PT) {
+        if (kx < 15) {  // step k+1 lives in the same 16-block
+          update(std::integral_constant<int, kb>{}, std::true_type{});
+          publish(std::integral_constant<int, kb>{}, k + 1);
+          update(std::integral_constant<int, kb>{}, std::false_type{});
+        } else {
+          constexpr int NB = (kb < 7) ? kb + 1 : 7;
+          update(std::integral_constant<int, NB>{}, std::true_type{});
+          publish(std::integral_constant<int, NB>{}, k + 1);
+          update(std::integral_constant<int, NB>{}, std::false_type{});
+        }
+      } else {
+        update(std::integral_constant<int, 99>{}, std::false_type{});
+      }
+      PROBE(7, k, tid == 255);
+      if (ty == kx) {  // row k of W is final once scaled (its own update above was a no-op: li = 0 there)
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int c = tx + 16 * b;
-            if (b <= kb) w[kb][b] = (c < k) ? w[kb][b] * rinv : ((c == k) ? rinv : w[kb][b]);
-          }
+        for (int b = 0; b < 8; ++b) {
+          const int c = tx + 16 * b;
+          if (b <= kb) w[kb][b] = (c < k) ? w[kb][b] * rinv : ((c == k) ? rinv : w[kb][b]);
         }
       }
     }
-  }
+  };
+  block_steps(std::integral_constant<int, 0>{});
+  block_steps(std::integral_constant<int, 1>{});
+  block_steps(std::integral_constant<int, 2>{});
+  block_steps(std::integral_constant<int, 3>{});
+  block_steps(std::integral_constant<int, 4>{});
+  block_steps(std::integral_constant<int, 5>{});
+  block_steps(std::integral_constant<int, 6>{});
+  block_steps(std::integral_constant<int, 7>{});
   if (stop) return;
 
   // L back to the matrix (the strict upper part of the tile is zeroed) and W = L^-1, 128 x 128
