@@ -58,8 +58,9 @@ SIGNATURES = {
     "cocons_dist_npad": (_i64, [_vp]),
     "cocons_dist_panel_elems": (_i64, [_vp, _i64]),
     "cocons_dist_assemble": (ctypes.c_int, [_vp, _dp, _dp, _dp]),
-    "cocons_dist_factor_panel": (ctypes.c_int, [_vp, _i64]),
-    "cocons_dist_pack_panel": (ctypes.c_int, [_vp, _i64, _vp]),
+    "cocons_dist_side_stream": (_vp, [_vp]),
+    "cocons_dist_factor_panel": (ctypes.c_int, [_vp, _i64, ctypes.c_int]),
+    "cocons_dist_pack_panel": (ctypes.c_int, [_vp, _i64, _vp, ctypes.c_int]),
     "cocons_dist_update": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64]),
     "cocons_dist_fill_rhs": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ip]),
     "cocons_dist_solve_block": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, ctypes.c_int]),

@@ -74,6 +74,8 @@ class CudaPanelOps:
                                                  self.h))
         self.npanels = int(_lib.lib().cocons_dist_npanels(self.h))
         self.n_pad = int(_lib.lib().cocons_dist_npad(self.h))
+        self.main = torch.cuda.current_stream()
+        self.side = torch.cuda.ExternalStream(int(_lib.lib().cocons_dist_side_stream(self.h)), device=self.device)
 
     def close(self):
         if self.h is not None and self.h.value:
@@ -93,11 +95,20 @@ class CudaPanelOps:
     def assemble(self, theta6, limits, mean):
         _lib.check(_lib.lib().cocons_dist_assemble(self.h, _lib.ptr(theta6), _lib.ptr(limits), _lib.ptr(mean)))
 
-    def factor_panel(self, K):
-        _lib.check(_lib.lib().cocons_dist_factor_panel(self.h, K))
+    def factor_panel(self, K, side=False):
+        _lib.check(_lib.lib().cocons_dist_factor_panel(self.h, K, int(side)))
 
-    def pack_panel(self, K, buf):
-        _lib.check(_lib.lib().cocons_dist_pack_panel(self.h, K, buf.data_ptr()))
+    def pack_panel(self, K, buf, side=False):
+        _lib.check(_lib.lib().cocons_dist_pack_panel(self.h, K, buf.data_ptr(), int(side)))
+
+    # stream plumbing for the look-ahead: the side stream waits for what the main stream has queued so far
+    def side_after_main(self):
+        ev = self.torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+
+    def on_side(self):
+        return self.torch.cuda.stream(self.side)
 
     def update(self, K, buf, lo, hi):
         _lib.check(_lib.lib().cocons_dist_update(self.h, K, buf.data_ptr(), lo, hi))
@@ -147,7 +158,9 @@ class DistributedDenseLikelihood:
         self.close()
 
     def owner(self, K):
-        return K % self.world
+        """Snake deal (0..N-1, N-1..0, ...), matching csrc/dist.cu: evens out the per-step update work."""
+        pos = K % self.world
+        return self.world - 1 - pos if (K // self.world) & 1 else pos
 
     def set_xbetas(self, xb):
         self.ops.set_xbetas(xb)
@@ -160,6 +173,17 @@ class DistributedDenseLikelihood:
         return self.dist.broadcast(self.bufs[K % 2][:count], src=self._global(self.owner(K)), group=self.group,
                                    async_op=async_op)
 
+    class _SideDone:
+        """world == 1: stands in for the broadcast handle - the main stream waits for the side stream"""
+
+        def __init__(self, ops):
+            self.ops = ops
+            self.ev = ops.torch.cuda.Event()
+            self.ev.record(ops.side)
+
+        def wait(self):
+            self.ops.main.wait_event(self.ev)
+
     def _global(self, rank_in_group):
         if self.group is None:
             return rank_in_group
@@ -167,7 +191,14 @@ class DistributedDenseLikelihood:
 
     # -- factorisation with one-panel look-ahead ------------------------------------------
     def factor(self, theta6, limits, mean=None):
+        """Right-looking factorisation with one-panel look-ahead.  Step K on every rank:
+             main stream : wait for panel K | (owner of K+1: apply update K to panel K+1) | apply update K
+                           to the rest of the rank's panels
+             side stream : (owner of K+1: factor panel K+1, pack it) | broadcast of panel K+1
+           The side stream has high priority, so the small panel kernels and the NCCL broadcast overlap
+           the main stream's DMMA updates; buffers alternate (K mod 2)."""
         ops, me = self.ops, self.rank
+        two_streams = hasattr(ops, "on_side")
         ops.assemble(theta6, limits, mean)
         if self.owner(0) == me:
             ops.factor_panel(0)
@@ -175,16 +206,32 @@ class DistributedDenseLikelihood:
         work = self._bcast(0, async_op=True)
         for K in range(self.npanels):
             if work is not None:
-                work.wait()  # the compute stream now waits for panel K
+                work.wait()  # the main stream now waits for panel K
             nxt = K + 1
             work = None
-            if nxt < self.npanels:
-                if self.owner(nxt) == me:  # look-ahead: next panel first, then ship it
+            if nxt >= self.npanels:
+                break
+            if not two_streams:  # CPU stand-in ops of the tests: same order, one queue
+                if self.owner(nxt) == me:
                     ops.update(K, self.bufs[K % 2], nxt, nxt + 1)
                     ops.factor_panel(nxt)
                     ops.pack_panel(nxt, self.bufs[nxt % 2])
                 work = self._bcast(nxt, async_op=True)
                 ops.update(K, self.bufs[K % 2], nxt + 1, self.npanels)
+                continue
+            if self.owner(nxt) == me:
+                ops.update(K, self.bufs[K % 2], nxt, nxt + 1)
+            # everything queued on main so far (all of update K-1, the look-ahead piece of update K) precedes
+            # the side-stream work: panel K+1 is current, and bufs[(K+1) % 2] is no longer being read
+            ops.side_after_main()
+            if self.owner(nxt) == me:
+                ops.factor_panel(nxt, side=True)
+                ops.pack_panel(nxt, self.bufs[nxt % 2], side=True)
+            with ops.on_side():
+                work = self._bcast(nxt, async_op=True)
+                if work is None:
+                    work = self._SideDone(ops)
+            ops.update(K, self.bufs[K % 2], nxt + 1, self.npanels)
 
     # -- solves + reductions --------------------------------------------------------------
     def terms(self, kind, theta_list, smooth_limits, mean=None):

@@ -169,8 +169,9 @@ int64_t cocons_dist_npanels(cocons_dist* ctx);
 int64_t cocons_dist_npad(cocons_dist* ctx);
 int64_t cocons_dist_panel_elems(cocons_dist* ctx, int64_t K);
 int cocons_dist_assemble(cocons_dist* ctx, const double* theta6, const double* smooth_limits, const double* mean_p);
-int cocons_dist_factor_panel(cocons_dist* ctx, int64_t K);
-int cocons_dist_pack_panel(cocons_dist* ctx, int64_t K, void* dst);
+void* cocons_dist_side_stream(cocons_dist* ctx);
+int cocons_dist_factor_panel(cocons_dist* ctx, int64_t K, int side);
+int cocons_dist_pack_panel(cocons_dist* ctx, int64_t K, void* dst, int side);
 int cocons_dist_update(cocons_dist* ctx, int64_t K, const void* src, int64_t J_lo, int64_t J_hi);
 int cocons_dist_fill_rhs(cocons_dist* ctx, int kind, void* rhs, int* nr_out);
 int cocons_dist_solve_block(cocons_dist* ctx, int64_t K, const void* bK, const void* tK, void* acc, void* Y, int nr);

@@ -34,6 +34,10 @@ class NumpyPanelOps(_NoSync):
     def close(self):
         pass
 
+    def owner(self, K):
+        pos = K % self.world
+        return self.world - 1 - pos if (K // self.world) & 1 else pos
+
     def width(self, K):
         return min(PANEL, self.n_pad - K * PANEL)
 
@@ -52,10 +56,10 @@ class NumpyPanelOps(_NoSync):
         S[: self.n, : self.n] = cov.cov_rns(th, self.locs, self.X, limits)
         self.mean = None if mean is None else np.asarray(mean, float)
         self.cols = {K: S[:, K * PANEL:K * PANEL + self.width(K)].copy()
-                     for K in range(self.rank, self.npanels, self.world)}
+                     for K in range(self.npanels) if self.owner(K) == self.rank}
 
     def factor_panel(self, K):
-        assert K % self.world == self.rank
+        assert self.owner(K) == self.rank
         c, r0, w = self.cols[K], K * PANEL, self.width(K)
         try:
             L = np.linalg.cholesky(c[r0:r0 + w, :])
@@ -76,7 +80,7 @@ class NumpyPanelOps(_NoSync):
             return
         P = buf.numpy()[: rows * self.width(K)].reshape(rows, self.width(K), order="F")
         for J in range(max(lo, K + 1), min(hi, self.npanels)):
-            if J % self.world != self.rank:
+            if self.owner(J) != self.rank:
                 continue
             off = J * PANEL - (K + 1) * PANEL
             self.cols[J][J * PANEL:, :] -= P[off:, :] @ P[off:off + self.width(J), :].T

@@ -44,8 +44,11 @@ def main():
         sys.path.insert(0, ".")
         import bench
         locs, X, z = bench.synthetic(args.n)
+        sampler = bench.ClockSampler(local) if rank == 0 else None
         with DistributedDenseLikelihood(locs, X, z) as d:
             for rep in range(args.reps):
+                if sampler is not None and rep == args.reps - 1:
+                    sampler.start()
                 t0 = time.perf_counter()
                 t = d.terms(_lib.ML, bench.theta_at(rep, 0), bench.LIMITS, bench.THETA["mean"])
                 wall = time.perf_counter() - t0
@@ -53,6 +56,8 @@ def main():
             out["large"] = {"n": args.n, "wall_s": wall, **ph,
                             "chol_tflops_all_gpus": bench.flops_chol(args.n) / ph["assemble_factor_s"] / 1e12,
                             "value": args.n * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0])}
+            if sampler is not None:
+                out["large"]["clocks_rank0"] = sampler.stop()
     if rank == 0:
         print("DIST_CHECK " + json.dumps(out))
     if dist.is_initialized():
