@@ -224,8 +224,12 @@ __global__ void __launch_bounds__(kAsmTile, 8) assemble_lower_kernel(int64_t n, 
   __syncthreads();
   if (I >= n_out) return;
   const bool diag_tile = (tr == tc);
-  const int jend = diag_tile ? tid : (kAsmTile - 1);
-  for (int j = 0; j <= jend; ++j) {
+  // small problems: gridDim.z CTAs share a tile, each taking a slice of its 128 columns, so that a
+  // handful of tiles still spreads over all SMs
+  const int cw = kAsmTile / (int)gridDim.z;
+  const int jlo = (int)blockIdx.z * cw;
+  const int jend = min(diag_tile ? tid : (kAsmTile - 1), jlo + cw - 1);
+  for (int j = jlo; j <= jend; ++j) {
     const int64_t J = J0 + j;
     if (J >= n_out) break;
     double v;
@@ -378,7 +382,9 @@ static void launch_assemble_any(int64_t n, int64_t n_out, SiteTable T, double gl
 void launch_assemble_lower(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
                            double* C, int64_t ld, cudaStream_t st) {
   const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
-  launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, C, ld, 0, 0, dim3((unsigned)(nt * (nt + 1) / 2)), st);
+  const int64_t tiles = nt * (nt + 1) / 2;
+  const unsigned slices = tiles < 2400 ? 8u : (tiles < 9600 ? 4u : 1u);  // ~1200 CTAs fit the GPU at once
+  launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, C, ld, 0, 0, dim3((unsigned)tiles, 1, slices), st);
 }
 
 // column panel [col_tile0, col_tile0 + ncol_tiles) of the lower triangle into a slab whose first
