@@ -22,6 +22,7 @@ from .api import (  # noqa: F401
     fd_value_and_grad,
     getCovMatrix,
     getDesignMatrix,
+    getHessian,
     getModelLists,
     getScale,
     is_formula,

@@ -518,6 +518,39 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     return coco_object
 
 
+def getHessian(coco_object, ncores="auto", eps=np.finfo(float).eps ** 0.25, device=0):
+    """R/getFunctions.R:925-1034, dense branch: forward-difference Hessian of the NEGATIVE log-likelihood
+    at the fitted parameters, H[j,i] = 0.5 (f11 - f01 - f10 + f00) / eps^2 with f = -2 loglik (for "pml"
+    fits on the full likelihood, as there).  The reference farms three evaluations per index pair over a
+    PSOCK cluster; here the p + p(p+1)/2 distinct points are evaluated as one batch on the GPU(s)."""
+    if coco_object.info.get("optim.type") == "reml":
+        raise NotImplementedError("reml hessian not implemented yet.")  # as the reference
+    par = np.asarray(coco_object.output["par"], dtype=np.float64)
+    p = par.shape[0]
+    dm = getDesignMatrix(coco_object.model_list, coco_object.data)
+    X = getScale(dm["model.matrix"], coco_object.info["mean.vector"], coco_object.info["sd.vector"])["std.covs"]
+    n = coco_object.z.shape[0]
+    lim = coco_object.info["smooth.limits"]
+    lam = (coco_object.info["lambda.Sigma"], coco_object.info["lambda.betas"], coco_object.info["lambda.reg"])
+    if ncores == "auto":
+        ncores = max(1, min(8, int(4e9 // (8 * n * n))))
+    singles = [par + eps * np.eye(p)[j] for j in range(p)]
+    pairs = [(j, i) for j in range(p) for i in range(j, p)]
+    doubles = [par + eps * (np.eye(p)[j] + np.eye(p)[i]) for j, i in pairs]
+    with DenseLikelihoodPool(coco_object.locs, X, coco_object.z, size=int(ncores), device=device) as pool:
+        def fn_on(c, theta):
+            return _objective(_lib.ML, theta, dm["par.pos"], None, None, lim, None, n, lam, True, ctx=c)
+        vals = pool.map(fn_on, [par] + singles + doubles)
+    f00 = vals[0] if coco_object.info.get("optim.type") == "pml" else coco_object.output["value"]
+    f1 = vals[1:1 + p]
+    H = np.zeros((p, p))
+    for (j, i), f11 in zip(pairs, vals[1 + p:]):
+        H[j, i] = 0.5 * ((f11 - f1[j] - f1[i] + f00) / (eps * eps))
+    H = H + H.T
+    H[np.diag_indices(p)] /= 2
+    return H
+
+
 def cocoPredict(coco_object, newdataset, newlocs, type="mean", index_pred=0, device=0):
     """R/predict.R:84-188, dense branch: kriging mean and (type "pred") standard deviation.  The
     reference solves with LU (`solve`); here the Cholesky factor on the device is used."""

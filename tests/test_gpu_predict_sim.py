@@ -138,3 +138,33 @@ def test_pml_fit_recovers_betas(datasets):
     Si = np.linalg.inv(S)
     gls = np.linalg.solve(X.T @ Si @ X, X.T @ Si @ H[:, 4])
     assert np.allclose(fit.output["par"][:3], gls, rtol=1e-7, atol=1e-9)
+
+
+def test_hessian_mirrors_the_reference_scheme(datasets):
+    """getHessian (R/getFunctions.R:925-1034): same forward-difference formula, evaluated on the GPU pool;
+    compared with the identical formula driven by the CPU oracle's objective."""
+    H0 = datasets["holes_training"][:80]
+    data = {"x": H0[:, 0], "y": H0[:, 1], "cov_x": H0[:, 2], "cov_y": H0[:, 3]}
+    ml = {"mean": 0, "std.dev": "~ 1 + cov_x", "scale": "~ 1", "aniso": 0, "tilt": 0, "smooth": 1.5,
+          "nugget": -np.inf}
+    obj = cb.coco("dense", data, H0[:, :2], H0[:, 4], ml)
+    dm = cb.getDesignMatrix(obj.model_list, obj.data)
+    sc = cb.getScale(dm["model.matrix"])
+    par = np.array([0.3, 0.1, -1.2])
+    lam = (0.0, 0.0, 0.0)
+    f = lambda th: rmirror.neg2loglik(th, dm["par.pos"], H0[:, :2], sc["std.covs"], [1.5, 1.5], H0[:, 4], 80, lam)  # noqa: E731
+    obj.output = {"par": par, "value": f(par)}
+    obj.info.update({"mean.vector": sc["mean.vector"], "sd.vector": sc["sd.vector"], "optim.type": "ml"})
+    Hg = cb.getHessian(obj)
+    eps = np.finfo(float).eps ** 0.25
+    p = 3
+    Hr = np.zeros((p, p))
+    for j in range(p):
+        for i in range(j, p):
+            e1, e2 = np.eye(p)[j] * eps, np.eye(p)[i] * eps
+            Hr[j, i] = 0.5 * (f(par + e1 + e2) - f(par + e1) - f(par + e2) + f(par)) / eps ** 2
+    Hr = Hr + Hr.T
+    Hr[np.diag_indices(p)] /= 2
+    assert np.array_equal(Hg, Hg.T)
+    # both are differences of O(1e2) values divided by eps^2 = 1.5e-8: agreement to ~1e-5 of |f|/eps^2 scale
+    assert np.max(np.abs(Hg - Hr)) < 1e-3 * max(1.0, np.max(np.abs(Hr)))
