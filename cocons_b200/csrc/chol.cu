@@ -90,16 +90,60 @@ __host__ __device__ __forceinline__ int64_t total_tiles(int ni, int njc, int low
   return total;
 }
 
+// O(1) inverse of the numbering above (a CTA decodes its tile once; a linear walk over the bands
+// would cost microseconds for the far-down tiles of a 1500-band-row update).
+//   bands [0, rt): complete triangle part      count(r) = 256 W r + 136 W   (h = 16)
+//   band rt (at most one): triangle clipped by njc or by the last, shorter band - walked directly
+//   bands after it: rectangles of h x njc
 template <int W>
-__device__ __forceinline__ void tile_decode(int64_t t, int ni, int njc, int lower_only, int& bi, int& bj) {
-  int r = 0, full_cols = 0;
-  for (;; ++r) {
-    const int64_t cnt = band_tiles<W>(r, ni, njc, lower_only, &full_cols);
-    if (t < cnt) break;
-    t -= cnt;
+__host__ __device__ __forceinline__ void tile_decode(int64_t t, int ni, int njc, int lower_only, int& bi, int& bj) {
+  const int nbands = (ni + kBandRows - 1) / kBandRows;
+  int r;
+  if (!lower_only) {
+    r = (int)(t / ((int64_t)kBandRows * njc));
+    if (r > nbands - 1) r = nbands - 1;
+    t -= (int64_t)r * kBandRows * njc;
+    const int r0 = r * kBandRows;
+    const int h = (ni - r0 < kBandRows) ? ni - r0 : kBandRows;
+    bj = (int)(t / h);
+    bi = r0 + (int)(t % h);
+    return;
+  }
+  // number of leading bands that are full height and whose triangle is not clipped by njc
+  int rt = njc / (kBandRows * W);
+  const int full_height = ni / kBandRows;
+  if (rt > full_height) rt = full_height;
+  const int64_t per_a = 128 * W, per_b = 136 * W;  // S(r) = per_a r (r - 1) + per_b r  tiles before band r
+  auto before = [&](int rr) { return per_a * rr * (int64_t)(rr - 1) + per_b * rr; };
+  if (t < before(rt)) {
+    const double a = (double)per_a, b = (double)(per_b - per_a);
+    r = (int)((-b + sqrt(b * b + 4.0 * a * (double)t)) / (2.0 * a));
+    if (r < 0) r = 0;
+    while (r + 1 <= rt && before(r + 1) <= t) ++r;
+    while (before(r) > t) --r;
+    t -= before(r);
+  } else {
+    t -= before(rt);
+    r = rt;
+    int dummy;
+    for (;; ++r) {  // at most two irregular bands, then rectangles in closed form
+      const int64_t cnt = band_tiles<W>(r, ni, njc, 1, &dummy);
+      if (t < cnt) break;
+      t -= cnt;
+      const int r0n = (r + 1) * kBandRows;
+      if (W * r0n >= njc && ni - r0n >= kBandRows) {  // from here on: full-height rectangles h x njc
+        const int64_t rect = (int64_t)kBandRows * njc;
+        int skip = (int)(t / rect);
+        const int max_skip = (ni - r0n) / kBandRows - 1;  // keep the last (possibly shorter) band for the walk
+        if (skip > max_skip) skip = max_skip < 0 ? 0 : max_skip;
+        r += skip;
+        t -= (int64_t)skip * rect;
+      }
+    }
   }
   const int r0 = r * kBandRows;
   const int h = (ni - r0 < kBandRows) ? ni - r0 : kBandRows;
+  const int full_cols = (W * r0 < njc) ? W * r0 : njc;
   if (t < (int64_t)h * full_cols) {
     bj = (int)(t / h);
     bi = r0 + (int)(t % h);

@@ -147,6 +147,9 @@ class DistributedDenseLikelihood:
         biggest = max([ops.panel_elems(K) for K in range(self.npanels)] + [1])
         self.bufs = [ops.buffer(biggest), ops.buffer(biggest)]
         self.last_phase_s = {}
+        import os
+        self.profile = bool(os.environ.get("COCONS_DIST_PROFILE"))  # per-step broadcast-wait times (debugging)
+        self.last_wait_ms = None
 
     def close(self):
         self.ops.close()
@@ -204,9 +207,16 @@ class DistributedDenseLikelihood:
             ops.factor_panel(0)
             ops.pack_panel(0, self.bufs[0])
         work = self._bcast(0, async_op=True)
+        prof = [] if (two_streams and self.profile) else None
         for K in range(self.npanels):
+            if prof is not None:
+                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                e0.record(ops.main)
             if work is not None:
                 work.wait()  # the main stream now waits for panel K
+            if prof is not None:
+                e1.record(ops.main)
+                prof.append((e0, e1))
             nxt = K + 1
             work = None
             if nxt >= self.npanels:
@@ -232,6 +242,11 @@ class DistributedDenseLikelihood:
                 if work is None:
                     work = self._SideDone(ops)
             ops.update(K, self.bufs[K % 2], nxt + 1, self.npanels)
+        if prof is not None:
+            self.torch.cuda.synchronize()
+            waits = [a.elapsed_time(b) for a, b in prof]
+            self.last_wait_ms = {"total": float(sum(waits)), "first_100": float(sum(waits[:100])),
+                                 "last_100": float(sum(waits[-100:])), "max": float(max(waits))}
 
     # -- solves + reductions --------------------------------------------------------------
     def terms(self, kind, theta_list, smooth_limits, mean=None):

@@ -58,6 +58,8 @@ def main():
                             "value": args.n * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0])}
             if sampler is not None:
                 out["large"]["clocks_rank0"] = sampler.stop()
+            if d.last_wait_ms is not None:
+                out["large"]["bcast_wait_ms_rank0"] = d.last_wait_ms
     if rank == 0:
         print("DIST_CHECK " + json.dumps(out))
     if dist.is_initialized():
