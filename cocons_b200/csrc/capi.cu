@@ -678,17 +678,29 @@ int cocons_factor(cocons_ctx* c, int par, const double* theta6, const double* li
   return 0;
 }
 
-// T = C L^-T for a block of prediction sites, in place on dC (mp x n_pad, ld = mp):
-// column tile J:  T_J = C_J inv(L_JJ)^T ;  C_K -= T_J L_KJ^T for K > J.
+// T = C L^-T for a block of prediction sites, in place on dC (mp x n_pad, ld = mp), right-looking with the
+// same two-level blocking as the factorisation: inside a 512-wide panel, column tile J gets
+// T_J = C_J inv(L_JJ)^T and updates the rest of the panel (K = 128); the columns right of the panel are then
+// updated once with K = 512, which is where the flops are.
 static void right_solve_lt(cocons_ctx* c, double* dC, int64_t mp) {
-  const int64_t np = c->n_pad, nt = np / kTile;
-  for (int64_t J = 0; J < nt; ++J) {
-    double* CJ = dC + J * kTile * mp;
-    launch_gemm_nt(1, mp, kTile, kTile, CJ, mp, c->ws.winv + J * (int64_t)kTile * kTile, kTile, CJ, mp, 0, c->stream);
-    const int64_t rest = np - (J + 1) * kTile;
-    if (rest > 0)
-      launch_gemm_nt(0, mp, rest, kTile, CJ, mp, c->dA + J * kTile * np + (J + 1) * kTile, np, CJ + kTile * mp, mp, 0,
+  static int outer_env = -1;
+  if (outer_env < 0) { const char* e = getenv("COCONS_PRED_OUTER"); outer_env = e ? atoi(e) : 4; }
+  const int64_t np = c->n_pad, nt = np / kTile, outer = outer_env;
+  for (int64_t J0 = 0; J0 < nt; J0 += outer) {
+    const int64_t jb = std::min<int64_t>(outer, nt - J0);
+    for (int64_t J = J0; J < J0 + jb; ++J) {
+      double* CJ = dC + J * kTile * mp;
+      launch_gemm_nt(1, mp, kTile, kTile, CJ, mp, c->ws.winv + J * (int64_t)kTile * kTile, kTile, CJ, mp, 0,
                      c->stream);
+      const int64_t rest = (J0 + jb - J - 1) * kTile;  // remaining columns of this panel
+      if (rest > 0)
+        launch_gemm_nt(0, mp, rest, kTile, CJ, mp, c->dA + J * kTile * np + (J + 1) * kTile, np, CJ + kTile * mp, mp,
+                       0, c->stream);
+    }
+    const int64_t done = (J0 + jb) * kTile, trail = np - done;
+    if (trail > 0)  // C[:, done:] -= T[:, panel] L[done:, panel]^T
+      launch_gemm_nt(0, mp, trail, jb * kTile, dC + J0 * kTile * mp, mp, c->dA + J0 * kTile * np + done, np,
+                     dC + done * mp, mp, 0, c->stream);
   }
 }
 
