@@ -147,6 +147,11 @@ struct cocons_dist {
   double* tmp = nullptr;   // kPanelW x 2*kDistMaxRhs scratch for the diagonal-block solve
   double* dScal = nullptr;
   CholWorkspace ws{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the per-panel launches of one update are independent: they are spread over a few streams so that
+  // the tail of one launch is filled by the head of the next
+  static constexpr int kUpdStreams = 3;
+  cudaStream_t upd[kUpdStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kUpdStreams] = {nullptr, nullptr, nullptr};
   int mode = 0;
   double nu_fixed = 0, global_range = 1, lim[2] = {0, 0};
   int64_t width(int64_t K) const { return std::min<int64_t>(kPanelW, n_pad - K * kPanelW); }
@@ -167,6 +172,11 @@ void cocons_dist_destroy(cocons_dist* c) {
   cudaFree(c->dX), cudaFree(c->dLocs), cudaFree(c->dZ), cudaFree(c->dXb), cudaFree(c->dTheta), cudaFree(c->dSite);
   cudaFree(c->dOrig), cudaFree(c->slab), cudaFree(c->tmp), cudaFree(c->dScal);
   chol_workspace_destroy(&c->ws);
+  for (int i = 0; i < cocons_dist::kUpdStreams; ++i) {
+    if (c->upd[i]) cudaStreamDestroy(c->upd[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   delete c;
 }
 
@@ -207,6 +217,10 @@ int cocons_dist_create(int device, int rank, int world, int64_t n, int64_t p, in
             cudaMalloc(&c->tmp, sizeof(double) * kPanelW * 2 * kDistMaxRhs) == cudaSuccess &&
             cudaMalloc(&c->dScal, sizeof(double) * (kDistMaxRhs * kDistMaxRhs * 300 + 16)) == cudaSuccess &&
             chol_workspace_create(np, &c->ws) == 0;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < cocons_dist::kUpdStreams; ++i)
+    ok = cudaStreamCreateWithFlags(&c->upd[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     set_error("dist_create: out of device memory (n_pad=%lld, local panels=%lld)", (long long)np,
               (long long)c->nlocal);
@@ -332,12 +346,30 @@ int cocons_dist_update(cocons_dist* c, int64_t K, const void* src, int64_t J_lo,
   const double* P = (const double*)src;
   if (J_lo <= K) J_lo = K + 1;
   if (J_hi > c->npanels) J_hi = c->npanels;
+  static int nstreams = -1;  // COCONS_DIST_UPD_STREAMS=1 keeps every update on the main stream (A/B knob)
+  if (nstreams < 0) {
+    const char* e = getenv("COCONS_DIST_UPD_STREAMS");
+    nstreams = e ? std::max(1, std::min(atoi(e), (int)cocons_dist::kUpdStreams)) : cocons_dist::kUpdStreams;
+  }
+  int launched = 0;
   for (int64_t J = J_lo; J < J_hi; ++J) {
     if (c->owner(J) != c->rank) continue;
     const int64_t off = J * kPanelW - r0;  // first row of panel J inside the packed buffer
     const double* Pj = P + off;
+    cudaStream_t s = c->stream;
+    if (nstreams > 1) {
+      const int sidx = launched % nstreams;
+      if (launched == 0) COCONS_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+      if (launched < nstreams) COCONS_CUDA_TRY(cudaStreamWaitEvent(c->upd[sidx], c->ev_fork, 0));
+      s = c->upd[sidx];
+    }
     launch_gemm_nt(0, c->n_pad - J * kPanelW, c->width(J), c->width(K), Pj, rows, Pj, rows,
-                   c->panel(J) + J * kPanelW, c->n_pad, 1, c->stream);
+                   c->panel(J) + J * kPanelW, c->n_pad, 1, s);
+    ++launched;
+  }
+  for (int i = 0; nstreams > 1 && i < launched && i < nstreams; ++i) {  // join
+    COCONS_CUDA_TRY(cudaEventRecord(c->ev_join[i], c->upd[i]));
+    COCONS_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }
   COCONS_CUDA_TRY(cudaGetLastError());
   return 0;
