@@ -11,6 +11,8 @@ from .api import (  # noqa: F401
     GetNeg2loglikelihood,
     GetNeg2loglikelihoodProfile,
     GetNeg2loglikelihoodREML,
+    GetNeg2loglikelihoodTaper,
+    GetNeg2loglikelihoodTaperProfile,
     NotPositiveDefinite,
     coco,
     cocoOptim,
@@ -19,6 +21,10 @@ from .api import (  # noqa: F401
     cov_rns,
     cov_rns_classic,
     cov_rns_pred,
+    cov_rns_taper,
+    cov_rns_taper_pred,
+    cov_wend1,
+    cov_wend2,
     fd_value_and_grad,
     getCovMatrix,
     getDesignMatrix,
@@ -26,7 +32,9 @@ from .api import (  # noqa: F401
     getModelLists,
     getScale,
     is_formula,
+    nearest_dist,
     reml_contrasts,
+    spam,
     sumsmoothlone,
 )
 

@@ -21,6 +21,7 @@ ASPECTS = ("std.dev", "scale", "aniso", "tilt", "smooth", "nugget")
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 _lp = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
 _i64 = ctypes.c_int64
 _vp = ctypes.c_void_p
 
@@ -39,6 +40,13 @@ SIGNATURES = {
     "cocons_ctx_set_z": (ctypes.c_int, [_vp, _dp]),
     "cocons_ctx_set_xbetas": (ctypes.c_int, [_vp, _i64, _dp]),
     "cocons_n2ll": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "cocons_cov_rns_taper": (ctypes.c_int, [_i64, _i64, _dp, _dp, _dp, _dp, _i32p, _i32p, _i64, _dp]),
+    "cocons_cov_rns_taper_pred": (ctypes.c_int, [_i64, _i64, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _i32p, _i32p, _i64,
+                                                 _dp]),
+    "cocons_ctx_set_taper": (ctypes.c_int, [_vp, _i32p, _i32p, _dp, _i64]),
+    "cocons_n2ll_taper": (ctypes.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "cocons_factor_taper": (ctypes.c_int, [_vp, _dp, _dp]),
+    "cocons_predict_taper": (ctypes.c_int, [_vp, _i64, _dp, _dp, _i32p, _i32p, _dp, _i64, _dp, _dp, _dp]),
     "cocons_profile_betas": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
     "cocons_factor": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp]),
     "cocons_predict": (ctypes.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp]),
@@ -116,6 +124,10 @@ def fmat(a, rows=None):
 
 def ptr(a):
     return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(_i32p)
 
 
 def pack_theta(theta, p):

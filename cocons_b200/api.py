@@ -66,6 +66,115 @@ def cov_rns_classic(theta, locs, x_covariates):
     return out
 
 
+def _pattern(colindices, rowpointers):
+    """spam's 1-based CSR slots as contiguous int32 (what INTEGER() of the slots points at)."""
+    ci = np.ascontiguousarray(np.asarray(colindices).astype(np.int32, copy=False))
+    rp = np.ascontiguousarray(np.asarray(rowpointers).astype(np.int32, copy=False))
+    return ci, rp
+
+
+def cov_rns_taper(theta, locs, x_covariates, colindices, rowpointers, smooth_limits):
+    """R/RcppExports.R:72-74 -> src/cocons_taper.cpp:151-433.  Returns the covariance entries on the pattern."""
+    locs, X = _lib.fmat(locs), _lib.fmat(x_covariates)
+    n, p = X.shape
+    th = _lib.pack_theta(theta, p)
+    lim = np.ascontiguousarray(np.asarray(smooth_limits, dtype=np.float64))
+    ci, rp = _pattern(colindices, rowpointers)
+    out = np.empty(ci.shape[0])
+    _lib.check(_lib.lib().cocons_cov_rns_taper(n, p, _lib.ptr(locs), _lib.ptr(X), _lib.ptr(th), _lib.ptr(lim),
+                                               _lib.iptr(ci), _lib.iptr(rp), ci.shape[0], _lib.ptr(out)))
+    return out
+
+
+def cov_rns_taper_pred(theta, locs, locs_pred, x_covariates, x_covariates_pred, colindices, rowpointers,
+                       smooth_limits):
+    """R/RcppExports.R:59-61 -> src/cocons_taper.cpp:17-139.  The pattern's rows are the prediction sites."""
+    locs, lp = _lib.fmat(locs), _lib.fmat(locs_pred)
+    X, Xp = _lib.fmat(x_covariates), _lib.fmat(x_covariates_pred)
+    n, p = X.shape
+    m = Xp.shape[0]
+    th = _lib.pack_theta(theta, p)
+    lim = np.ascontiguousarray(np.asarray(smooth_limits, dtype=np.float64))
+    ci, rp = _pattern(colindices, rowpointers)
+    out = np.empty(ci.shape[0])
+    _lib.check(_lib.lib().cocons_cov_rns_taper_pred(n, m, p, _lib.ptr(locs), _lib.ptr(lp), _lib.ptr(X), _lib.ptr(Xp),
+                                                    _lib.ptr(th), _lib.ptr(lim), _lib.iptr(ci), _lib.iptr(rp),
+                                                    ci.shape[0], _lib.ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------
+# the pieces of `spam` the sparse path touches (third-party in the reference:
+# spam >= 2.9.1, DESCRIPTION:21; absent here, restated from its documentation)
+# --------------------------------------------------------------------------
+class spam:
+    """The slots of a spam matrix the path reads: `entries`, 1-based `colindices` / `rowpointers`
+    (CSR, columns ascending within a row) and `dimension`."""
+
+    def __init__(self, entries, colindices, rowpointers, dimension):
+        self.entries = np.ascontiguousarray(np.asarray(entries, dtype=np.float64))
+        self.colindices, self.rowpointers = _pattern(colindices, rowpointers)
+        self.dimension = (int(dimension[0]), int(dimension[1]))
+
+    def copy(self):
+        return spam(self.entries.copy(), self.colindices, self.rowpointers, self.dimension)
+
+    def density(self):
+        return self.entries.shape[0] / (self.dimension[0] * self.dimension[1])
+
+    def toarray(self):
+        out = np.zeros(self.dimension)
+        rows = np.repeat(np.arange(self.dimension[0]), np.diff(self.rowpointers))
+        out[rows, self.colindices - 1] = self.entries
+        return out
+
+
+def nearest_dist(x, y=None, delta=1.0, upper=None):
+    """spam::nearest.dist(x, y, method = "euclidean", delta, upper = NULL) as the reference calls it
+    (R/optim.R:377, R/predict.R:219,233): the Euclidean distances not exceeding `delta`, rows = sites
+    of x, columns = sites of y (or x).  Coincident pairs and the diagonal are kept - the reference's
+    pair loop expects them (`ii == jj`, src/cocons_taper.cpp:227; coordinate equality, :89)."""
+    from scipy.spatial import cKDTree
+
+    if upper is not None:
+        raise NotImplementedError("only upper = NULL (the whole matrix) is used on this path")
+    x = np.asarray(x, dtype=np.float64)
+    yy = x if y is None else np.asarray(y, dtype=np.float64)
+    tx = cKDTree(x)
+    ty = tx if y is None else cKDTree(yy)
+    trip = tx.sparse_distance_matrix(ty, float(delta), output_type="ndarray")
+    order = np.lexsort((trip["j"], trip["i"]))
+    i, j, v = trip["i"][order], trip["j"][order], trip["v"][order]
+    rowpointers = np.concatenate([[0], np.cumsum(np.bincount(i, minlength=x.shape[0]))]) + 1
+    return spam(v, j + 1, rowpointers, (x.shape[0], yy.shape[0]))
+
+
+def _apply_on_entries(h, fun):
+    if isinstance(h, spam):
+        return spam(fun(h.entries), h.colindices, h.rowpointers, h.dimension)
+    return fun(np.asarray(h, dtype=np.float64))
+
+
+def cov_wend1(h, theta):
+    """spam::cov.wend1: theta = c(range, sill[, nugget]); sill (1 - d)^4_+ (1 + 4 d), d = h / range."""
+    rng, sill = float(theta[0]), float(theta[1]) if len(theta) > 1 else 1.0
+
+    def f(d):
+        d = d / rng
+        return sill * np.where(d < 1, (1 - d) ** 4 * (1 + 4 * d), 0.0)
+    return _apply_on_entries(h, f)
+
+
+def cov_wend2(h, theta):
+    """spam::cov.wend2: sill (1 - d)^6_+ (1 + 6 d + 35 d^2 / 3), d = h / range."""
+    rng, sill = float(theta[0]), float(theta[1]) if len(theta) > 1 else 1.0
+
+    def f(d):
+        d = d / rng
+        return sill * np.where(d < 1, (1 - d) ** 6 * (1 + 6 * d + 35 * d * d / 3), 0.0)
+    return _apply_on_entries(h, f)
+
+
 # --------------------------------------------------------------------------
 # parameter packing that stays on the host (R/getFunctions.R)
 # --------------------------------------------------------------------------
@@ -234,6 +343,43 @@ class DenseLikelihood:
                                           _lib.ctypes.byref(rank)))
         return {"logdet": logdet.value, "quad": quad, "logdet_w": ldw.value, "rank": rank.value}
 
+    def set_taper(self, ref_taper):
+        """Attach the taper of a sparse coco object (a `spam`: pattern + taper values, R/optim.R:376-379)."""
+        assert ref_taper.dimension == (self.n, self.n)
+        _lib.check(_lib.lib().cocons_ctx_set_taper(self._h, _lib.iptr(ref_taper.colindices),
+                                                   _lib.iptr(ref_taper.rowpointers), _lib.ptr(ref_taper.entries),
+                                                   ref_taper.entries.shape[0]))
+
+    def terms_taper(self, theta_list, smooth_limits, mean=None):
+        """One evaluation of the tapered model; returns dict(logdet, quad[r])."""
+        th = _lib.pack_theta(theta_list, self.p)
+        lim = np.ascontiguousarray(np.asarray(smooth_limits, dtype=np.float64))
+        mean_v = None if mean is None else np.ascontiguousarray(np.asarray(mean, dtype=np.float64))
+        logdet = _lib.ctypes.c_double()
+        quad = np.empty(self.r)
+        _lib.check(_lib.lib().cocons_n2ll_taper(self._h, _lib.ptr(th), _lib.ptr(lim), _lib.ptr(mean_v),
+                                                _lib.ctypes.byref(logdet), _lib.ptr(quad)))
+        return {"logdet": logdet.value, "quad": quad}
+
+    def factor_taper(self, theta_list, smooth_limits):
+        th = _lib.pack_theta(theta_list, self.p)
+        lim = np.ascontiguousarray(np.asarray(smooth_limits, dtype=np.float64))
+        _lib.check(_lib.lib().cocons_factor_taper(self._h, _lib.ptr(th), _lib.ptr(lim)))
+
+    def predict_taper(self, locs_pred, x_covariates_pred, pred_taper, resid, want_explained=True):
+        """`pred_taper`: the taper on the prediction pattern (m x n `spam`), before the covariance is multiplied in."""
+        lp, Xp = _lib.fmat(locs_pred), _lib.fmat(x_covariates_pred)
+        m = Xp.shape[0]
+        assert pred_taper.dimension == (m, self.n)
+        resid = np.ascontiguousarray(np.asarray(resid, dtype=np.float64))
+        sto = np.empty(m)
+        expl = np.empty(m) if want_explained else None
+        _lib.check(_lib.lib().cocons_predict_taper(self._h, m, _lib.ptr(lp), _lib.ptr(Xp),
+                                                   _lib.iptr(pred_taper.colindices), _lib.iptr(pred_taper.rowpointers),
+                                                   _lib.ptr(pred_taper.entries), pred_taper.entries.shape[0],
+                                                   _lib.ptr(resid), _lib.ptr(sto), _lib.ptr(expl)))
+        return sto, expl
+
     def profile_betas(self, kind):
         k = self.q if kind == _lib.PROFILE else self.p
         out = np.empty(k)
@@ -360,6 +506,48 @@ def reml_contrasts(mod_DM, z):
     return z - X @ np.linalg.solve(X.T @ X, X.T @ z)
 
 
+def _taper_terms(theta_list, ref_taper, locs, x_covariates, smooth_limits, z, n, safe, ctx):
+    try:
+        if ctx is not None:
+            return ctx.terms_taper(theta_list, smooth_limits, theta_list["mean"])
+        with DenseLikelihood(locs, x_covariates, _lib.fmat(z, rows=n)) as tmp:
+            tmp.set_taper(ref_taper)
+            return tmp.terms_taper(theta_list, smooth_limits, theta_list["mean"])
+    except NotPositiveDefinite:
+        if safe:
+            return None
+        raise ArithmeticError("Cholesky error")
+
+
+def GetNeg2loglikelihoodTaper(theta, par_pos, ref_taper, locs, x_covariates, smooth_limits, cholS, z, n, lambda_,
+                              safe=True, ctx=None):
+    """R/neg2loglikelihood.R:20-53.  `ref_taper` is the taper as a `spam`; `cholS` (spam's symbolic
+    Cholesky object there) is accepted and unused: the tapered matrix is factored densely on the GPU.
+    `ctx`: a DenseLikelihood that already had set_taper(ref_taper)."""
+    theta_list = getModelLists(theta, par_pos, "diff")
+    t = _taper_terms(theta_list, ref_taper, locs, x_covariates, smooth_limits, z, n, safe, ctx)
+    if t is None:
+        return 1e6  # :35-39
+    r = len(t["quad"])
+    sumlogs = sum(n * np.log(2 * np.pi) + 2 * t["logdet"] + qd for qd in t["quad"])  # :43-49
+    return sumlogs + _getPen(n * r, lambda_, theta_list, smooth_limits)
+
+
+def GetNeg2loglikelihoodTaperProfile(theta, par_pos, ref_taper, locs, x_covariates, smooth_limits, cholS, z, n,
+                                     lambda_, safe=True, ctx=None):
+    """R/neg2loglikelihood.R:73-108: the global variance profiled out (std.dev intercept set to 0, :78)."""
+    theta_list = getModelLists(theta, par_pos, "diff")
+    theta_list["std.dev"] = np.array(theta_list["std.dev"], dtype=np.float64)
+    theta_list["std.dev"][0] = 0.0
+    t = _taper_terms(theta_list, ref_taper, locs, x_covariates, smooth_limits, z, n, safe, ctx)
+    if t is None:
+        return 1e6
+    r = len(t["quad"])
+    sum_in = float(np.sum(t["quad"]))
+    return (r * n * np.log(2 * np.pi) + r * n + r * 2 * t["logdet"] + r * n * np.log(sum_in / (r * n)) +
+            _getPen(n * r, lambda_, theta_list, smooth_limits))  # :101-105
+
+
 # --------------------------------------------------------------------------
 # coco objects and the user-facing verbs
 # --------------------------------------------------------------------------
@@ -369,8 +557,6 @@ class coco:
     def __init__(self, type, data, locs, z, model_list, info=None, output=None):
         if type not in ("dense", "sparse"):
             raise ValueError("type must be 'dense' or 'sparse'")
-        if type == "sparse":
-            raise NotImplementedError("the tapered (sparse) model is outside this build's scope (SURVEY.md §8f N3)")
         self.type = type
         self.data = _columns(data)
         self.locs = np.asfortranarray(np.asarray(locs, dtype=np.float64))
@@ -393,16 +579,39 @@ class coco:
         if "smooth.limits" not in info:
             raise ValueError("info['smooth.limits'] is required when smooth is a formula")
         info["smooth.limits"] = np.asarray(info["smooth.limits"], dtype=np.float64)
+        if type == "sparse":  # .cocons.check.info, R/checkFunctions.R:316-331
+            if not callable(info.get("taper")):
+                raise ValueError("taper must be one compact supported function from package spam")
+            if info.get("delta") is None:
+                raise ValueError("taper type requires specifying a delta > 0")
+            if info["delta"] < 0:
+                raise ValueError("taper argument must be non-negative")
+        elif info.get("taper") is not None or info.get("delta") is not None:  # :334-339
+            raise ValueError("if type is dense taper / delta should not be specified")
         self.info = info
         self.output = dict(output or {})
 
 
 def getCovMatrix(coco_object):
-    """R/getFunctions.R:35-52 (dense, type 'global')."""
+    """R/getFunctions.R:35-80 (type 'global'; dense: the n x n matrix, sparse: a `spam`)."""
     x_covs = getScale(coco_object)["std.covs"]
     par_pos = getDesignMatrix(coco_object.model_list, coco_object.data)["par.pos"]
     theta_list = getModelLists(coco_object.output["par"], par_pos, "diff")
+    if coco_object.type == "sparse":  # :60-78: the tapered matrix, as a spam
+        ref_taper = _ref_taper(coco_object)
+        ref_taper.entries = ref_taper.entries * cov_rns_taper(theta_list, coco_object.locs, x_covs,
+                                                              ref_taper.colindices, ref_taper.rowpointers,
+                                                              coco_object.info["smooth.limits"])
+        return ref_taper
     return cov_rns(theta_list, coco_object.locs, x_covs, coco_object.info["smooth.limits"])
+
+
+def _ref_taper(coco_object, rows=None):
+    """info$taper(spam::nearest.dist(locs, delta = info$delta, upper = NULL), theta = c(delta, 1)),
+    R/optim.R:376-379; with `rows`, the prediction pattern of R/predict.R:233-235."""
+    d = coco_object.info["delta"]
+    dist = nearest_dist(coco_object.locs, delta=d) if rows is None else nearest_dist(rows, coco_object.locs, delta=d)
+    return coco_object.info["taper"](dist, (d, 1))
 
 
 def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None, batch=None):
@@ -488,6 +697,9 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     # contexts on one GPU; "auto" = as many as fit comfortably, none extra once one evaluation fills the GPU
     if ncores == "auto":
         ncores = max(1, min(8, int(4e9 // (8 * n * n))))
+    if coco_object.type == "sparse":
+        return _cocoOptim_sparse(coco_object, boundaries, dm, sc, mod_DM, init, lower, upper, ctrl, ndeps, forward,
+                                 int(ncores), safe, optim_type, device)
     with DenseLikelihoodPool(coco_object.locs, mod_DM, z, size=int(ncores), device=device) as pool:
         ctx = pool.ctxs[0]
         if optim_type == "pml":
@@ -511,6 +723,74 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
             ctx.factor(theta_list, lim)
             betas = ctx.profile_betas(_lib.PROFILE)
             par = np.concatenate([betas, par])
+    coco_object.output = {"par": par, "value": res.fun, "counts": res.nfev, "convergence": res.status,
+                          "message": res.message}
+    coco_object.info.update({"mean.vector": sc["mean.vector"], "sd.vector": sc["sd.vector"],
+                             "optim.type": optim_type, "safe": safe, "boundaries": boundaries})
+    return coco_object
+
+
+def _cocoOptim_sparse(coco_object, boundaries, dm, sc, mod_DM, init, lower, upper, ctrl, ndeps, forward, ncores, safe,
+                      optim_type, device):
+    """R/optim.R:366-690: the tapered model.  "ml" (:480-531) and "pml" (:533-688, global variance profiled
+    out and recovered after the fit).  The penalised two-step fit (:368-478) prunes the model through
+    .cocons.update.coco.first.step - validation/UI code outside this path - and is not mirrored."""
+    from scipy.optimize import minimize
+
+    if optim_type == "ml" and (coco_object.info["lambda.betas"] > 0 or coco_object.info["lambda.Sigma"] > 0):
+        raise NotImplementedError("penalised sparse fits (R/optim.R:368-478) are outside this build's scope")
+    if optim_type not in ("ml", "pml"):
+        raise ValueError("sparse coco objects support optim.type 'ml' and 'pml'")
+    n = coco_object.z.shape[0]
+    r = coco_object.z.shape[1]
+    lim = coco_object.info["smooth.limits"]
+    lam = (0.0, 0.0, coco_object.info["lambda.reg"])
+    ref_taper = _ref_taper(coco_object)
+    par_pos = dm["par.pos"]
+    is_free = {k: isinstance(v, np.ndarray) for k, v in par_pos.items()}
+    fn_ref = GetNeg2loglikelihoodTaper
+    if optim_type == "pml":
+        if not is_free["std.dev"]:
+            raise ValueError("at least a global sigma needs to be estimated for sparse pml coco objects.")
+        par_pos = dict(par_pos)
+        par_pos["std.dev"] = par_pos["std.dev"].copy()
+        par_pos["std.dev"][0] = False  # :566
+        first_sigma = int(dm["par.pos"]["mean"].sum()) if is_free["mean"] else 0  # 0-based :570-572
+        keep = np.arange(init.shape[0]) != first_sigma
+        init, lower, upper = init[keep], lower[keep], upper[keep]
+        fn_ref = GetNeg2loglikelihoodTaperProfile
+    with DenseLikelihoodPool(coco_object.locs, mod_DM, coco_object.z, size=ncores, device=device) as pool:
+        pool.set_taper(ref_taper)
+        ctx = pool.ctxs[0]
+
+        def fn_on(c, theta):
+            return fn_ref(theta, par_pos, ref_taper, None, None, lim, None, None, n, lam, safe, ctx=c)
+
+        res = minimize(lambda th: fd_value_and_grad(lambda t: fn_on(ctx, t), th, lower, upper, ndeps,
+                                                    forward=forward, batch=lambda pts: pool.map(fn_on, pts)),
+                       init, jac=True, method="L-BFGS-B", bounds=list(zip(lower, upper)), options=ctrl)
+        par = res.x
+        if optim_type == "pml":  # :590-662
+            theta_list = getModelLists(par, par_pos, "diff")
+            t = ctx.terms_taper(theta_list, lim, theta_list["mean"])  # resid' Sigma^-1 resid per column (:599-603)
+            sigma_0 = float(np.sum(t["quad"])) / (n * r)
+            nm = int(par_pos["mean"].sum()) if is_free["mean"] else 0
+            nsd = int(par_pos["std.dev"].sum())
+            first_scale = nm + nsd  # 0-based
+            g = par[first_scale] if is_free["scale"] else float(np.atleast_1d(par_pos["scale"])[0])
+            first_par, second_par = np.log(sigma_0) + g, np.log(sigma_0) - g
+            new = list(par[:nm]) + [first_par] + list(par[nm:nm + nsd])
+            pos = first_scale
+            if is_free["scale"]:
+                ns = int(par_pos["scale"].sum())
+                new += [second_par] + list(par[first_scale + 1:first_scale + ns])
+                pos = first_scale + ns
+            for k in ("smooth", "nugget"):
+                if is_free[k]:
+                    cnt = int(par_pos[k].sum())
+                    new += list(par[pos:pos + cnt])
+                    pos += cnt
+            par = np.asarray(new, dtype=np.float64)
     coco_object.output = {"par": par, "value": res.fun, "counts": res.nfev, "convergence": res.status,
                           "message": res.message}
     coco_object.info.update({"mean.vector": sc["mean.vector"], "sd.vector": sc["sd.vector"],
@@ -552,8 +832,9 @@ def getHessian(coco_object, ncores="auto", eps=np.finfo(float).eps ** 0.25, devi
 
 
 def cocoPredict(coco_object, newdataset, newlocs, type="mean", index_pred=0, device=0):
-    """R/predict.R:84-188, dense branch: kriging mean and (type "pred") standard deviation.  The
-    reference solves with LU (`solve`); here the Cholesky factor on the device is used."""
+    """R/predict.R:84-288: kriging mean and (type "pred") standard deviation, dense and sparse (tapered)
+    branches.  The reference solves with LU (`solve`) / spam's sparse solve; here the Cholesky factor on the
+    device is used."""
     if not coco_object.output:
         raise ValueError("coco object has not yet been fitted.")
     dm = getDesignMatrix(coco_object.model_list, coco_object.data)
@@ -564,8 +845,14 @@ def cocoPredict(coco_object, newdataset, newlocs, type="mean", index_pred=0, dev
     systematic = X_pred @ eff["mean"]
     resid = coco_object.z[:, index_pred] - X_std @ eff["mean"]
     with DenseLikelihood(coco_object.locs, X_std, coco_object.z, device=device) as ctx:
-        ctx.factor(eff, coco_object.info["smooth.limits"])
-        sto, expl = ctx.predict(newlocs, X_pred, resid, want_explained=(type == "pred"))
+        if coco_object.type == "sparse":  # R/predict.R:190-288: tapered Sigma and tapered cross-covariance
+            ctx.set_taper(_ref_taper(coco_object))
+            ctx.factor_taper(eff, coco_object.info["smooth.limits"])
+            sto, expl = ctx.predict_taper(newlocs, X_pred, _ref_taper(coco_object, rows=newlocs), resid,
+                                          want_explained=(type == "pred"))
+        else:
+            ctx.factor(eff, coco_object.info["smooth.limits"])
+            sto, expl = ctx.predict(newlocs, X_pred, resid, want_explained=(type == "pred"))
     out = {"systematic": systematic, "stochastic": sto}
     if type == "pred":  # :170-183
         u = 1 / np.exp(-(X_pred @ eff["std.dev"])) + np.exp(X_pred @ eff["nugget"]) - expl
@@ -610,7 +897,13 @@ def cocoSim(coco_object, pars=None, n=1, seed=None, standardize=True, type="clas
     if eps is None:
         eps = rng.standard_normal((nsites, n))
     with DenseLikelihood(coco_object.locs, std_coco, coco_object.z, device=device) as ctx:
-        ctx.factor(theta_to_fit, coco_object.info["smooth.limits"], type=type)
+        if coco_object.type == "sparse":
+            # R/sim.R:176-218.  The reference draws t(eps) %*% chol_spam(P Sigma P') un-permuted; any factor of
+            # Sigma gives the same distribution, and the draw here is L eps with the device's own factor.
+            ctx.set_taper(_ref_taper(coco_object))
+            ctx.factor_taper(theta_to_fit, coco_object.info["smooth.limits"])
+        else:
+            ctx.factor(theta_to_fit, coco_object.info["smooth.limits"], type=type)
         draws = ctx.sim(eps)
     return draws + (std_coco @ theta_to_fit["mean"])[:, None]
 
@@ -648,6 +941,10 @@ class DenseLikelihoodPool:
     def set_z(self, z):
         for c in self.ctxs:
             c.set_z(z)
+
+    def set_taper(self, ref_taper):
+        for c in self.ctxs:
+            c.set_taper(ref_taper)
 
     def map(self, fn, points):
         """[fn(ctx, point) for point in points], evaluated len(ctxs) at a time."""

@@ -209,7 +209,14 @@ struct cocons_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double ms[4] = {0, 0, 0, 0};
   double kernel_ms = 0, kernel_flops = 0;  // largest trailing-update launch of the last factorisation
+  // sparse (tapered) model: spam's CSR pattern (1-based, caller order), the taper values on it, and the
+  // caller-index -> sorted-position map
+  int *dTapCol = nullptr, *dTapRow = nullptr, *dInv = nullptr;
+  double* dTap = nullptr;
+  int64_t tap_nnz = 0;
+  bool factor_is_taper = false;
   SiteTable table() const { return SiteTable{dSite, n_pad, dOrig}; }
+  TaperTable taper_table() const { return TaperTable{dSite, n_pad}; }  // shares the per-site buffer
 };
 
 static int check_device(int device) {
@@ -373,6 +380,7 @@ void cocons_ctx_destroy(cocons_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->dX), cudaFree(c->dLocs), cudaFree(c->dZ), cudaFree(c->dXb), cudaFree(c->dTheta), cudaFree(c->dSite);
   cudaFree(c->dOrig), cudaFree(c->dA), cudaFree(c->dRhs);
+  cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dInv), cudaFree(c->dTap);
   chol_workspace_destroy(&c->ws);
   cudaFree(c->dGram);
   if (c->hStage) cudaFreeHost(c->hStage);
@@ -470,7 +478,7 @@ int cocons_ctx_set_xbetas(cocons_ctx* c, int64_t q, const double* xb) {
 
 // assembly + factorisation of the context's matrix; leaves events 0..2 recorded
 static int assemble_and_factor(cocons_ctx* c, int par, const double* theta6, const double* limits,
-                               const double* mean_p) {
+                               const double* mean_p, bool taper = false) {
   const int64_t p = c->p, np = c->n_pad;
   const double lim[2] = {limits ? limits[0] : 0.0, limits ? limits[1] : 0.0};
   c->mode = smooth_mode_for(par, (int)p, theta6, lim, &c->nu_fixed);
@@ -483,9 +491,20 @@ static int assemble_and_factor(cocons_ctx* c, int par, const double* theta6, con
     std::memset(c->hStage + 6 * p, 0, sizeof(double) * p);
   COCONS_CUDA_TRY(cudaMemcpyAsync(c->dTheta, c->hStage, sizeof(double) * 7 * p, cudaMemcpyHostToDevice, c->stream));
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-  launch_site_stage(c->n, np, (int)p, c->dX, np, c->dLocs, np, c->dTheta, lim[0], lim[1], c->mode, c->table(),
-                    c->stream);
-  launch_assemble_lower(c->n, np, c->table(), c->global_range, c->nu_fixed, c->mode, c->dA, np, c->stream);
+  if (taper) {
+    // tapered model: zero matrix, then taper[e] * cov[e] scattered onto the pattern (R/neg2loglikelihood.R:26-31)
+    launch_taper_site_stage(c->n, (int)p, c->dX, np, c->dLocs, np, c->dTheta, lim[0], lim[1], c->mode, 0,
+                            c->taper_table(), c->stream);
+    COCONS_CUDA_TRY(cudaMemsetAsync(c->dA, 0, sizeof(double) * np * np, c->stream));
+    launch_taper_pad_diag(c->n, np, c->dA, np, c->stream);
+    launch_taper_entries(0, c->tap_nnz, c->n, c->dTapCol, c->dTapRow, c->taper_table(), c->taper_table(), 1, c->mode,
+                         c->nu_fixed, TaperSink{TS_LOWER, nullptr, c->dTap, c->dInv, c->dA, np, 0}, c->stream);
+  } else {
+    launch_site_stage(c->n, np, (int)p, c->dX, np, c->dLocs, np, c->dTheta, lim[0], lim[1], c->mode, c->table(),
+                      c->stream);
+    launch_assemble_lower(c->n, np, c->table(), c->global_range, c->nu_fixed, c->mode, c->dA, np, c->stream);
+  }
+  c->factor_is_taper = taper;
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
   chol_factor(c->dA, np, np, c->ws, c->stream);
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
@@ -513,8 +532,8 @@ static int finish_timings(cocons_ctx* c) {
   return 0;
 }
 
-int cocons_n2ll(cocons_ctx* c, int kind, const double* theta6, const double* limits, const double* mean_p,
-                double* logdet, double* quad, double* logdet_w, int* rank_x) {
+static int n2ll_impl(cocons_ctx* c, int kind, const double* theta6, const double* limits, const double* mean_p,
+                     double* logdet, double* quad, double* logdet_w, int* rank_x, bool taper) {
   if (!c || !theta6 || !limits || !logdet || !quad || kind < COCONS_ML || kind > COCONS_REML || c->r <= 0) {
     set_error("n2ll: bad argument");
     return COCONS_ERR_ARG;
@@ -528,7 +547,7 @@ int cocons_n2ll(cocons_ctx* c, int kind, const double* theta6, const double* lim
     return COCONS_ERR_ARG;
   }
   cudaSetDevice(c->device);
-  int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, kind == COCONS_ML ? mean_p : nullptr);
+  int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, kind == COCONS_ML ? mean_p : nullptr, taper);
   if (rc) return rc;
   const int64_t np = c->n_pad, p = c->p;
   cudaStream_t st = c->stream;
@@ -603,6 +622,148 @@ int cocons_n2ll(cocons_ctx* c, int kind, const double* theta6, const double* lim
   }
   c->factor_valid = true;
   return finish_timings(c);
+}
+
+int cocons_n2ll(cocons_ctx* c, int kind, const double* theta6, const double* limits, const double* mean_p,
+                double* logdet, double* quad, double* logdet_w, int* rank_x) {
+  return n2ll_impl(c, kind, theta6, limits, mean_p, logdet, quad, logdet_w, rank_x, false);
+}
+
+// ---- sparse (tapered) model -------------------------------------------------
+
+// spam's 1-based CSR slots: rowpointers[0] == 1, non-decreasing, rowpointers[nrows] - 1 == nnz, columns in 1..ncols
+static int check_pattern(const char* who, const int32_t* colindices, const int32_t* rowpointers, int64_t nrows,
+                         int64_t ncols, int64_t nnz) {
+  if (!colindices || !rowpointers || nnz < 0 || nnz > INT32_MAX || rowpointers[0] != 1 ||
+      (int64_t)rowpointers[nrows] - 1 != nnz) {
+    set_error("%s: malformed pattern (rowpointers must start at 1 and end at nnz + 1)", who);
+    return COCONS_ERR_ARG;
+  }
+  for (int64_t i = 0; i < nrows; ++i)
+    if (rowpointers[i + 1] < rowpointers[i]) {
+      set_error("%s: rowpointers decrease at row %lld", who, (long long)i + 1);
+      return COCONS_ERR_ARG;
+    }
+  for (int64_t e = 0; e < nnz; ++e)
+    if (colindices[e] < 1 || colindices[e] > ncols) {
+      set_error("%s: colindices[%lld] = %d outside 1..%lld", who, (long long)e, colindices[e], (long long)ncols);
+      return COCONS_ERR_ARG;
+    }
+  return 0;
+}
+
+int cocons_ctx_set_taper(cocons_ctx* c, const int32_t* colindices, const int32_t* rowpointers,
+                         const double* taper_entries, int64_t nnz) {
+  if (!c || !taper_entries) {
+    set_error("ctx_set_taper: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  int rc = check_pattern("ctx_set_taper", colindices, rowpointers, c->n, c->n, nnz);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dTap);
+  c->dTapCol = c->dTapRow = nullptr, c->dTap = nullptr, c->tap_nnz = 0;
+  COCONS_CUDA_TRY(cudaMalloc(&c->dTapCol, sizeof(int) * std::max<int64_t>(nnz, 1)));
+  COCONS_CUDA_TRY(cudaMalloc(&c->dTapRow, sizeof(int) * (c->n + 1)));
+  COCONS_CUDA_TRY(cudaMalloc(&c->dTap, sizeof(double) * std::max<int64_t>(nnz, 1)));
+  if (!c->dInv) {
+    std::vector<int> inv((size_t)c->n);
+    for (int64_t s = 0; s < c->n; ++s) inv[(size_t)c->perm[(size_t)s]] = (int)s;
+    COCONS_CUDA_TRY(cudaMalloc(&c->dInv, sizeof(int) * c->n));
+    COCONS_CUDA_TRY(cudaMemcpy(c->dInv, inv.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
+  }
+  COCONS_CUDA_TRY(cudaMemcpy(c->dTapCol, colindices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+  COCONS_CUDA_TRY(cudaMemcpy(c->dTapRow, rowpointers, sizeof(int) * (c->n + 1), cudaMemcpyHostToDevice));
+  COCONS_CUDA_TRY(cudaMemcpy(c->dTap, taper_entries, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+  c->tap_nnz = nnz;
+  return 0;
+}
+
+int cocons_n2ll_taper(cocons_ctx* c, const double* theta6, const double* limits, const double* mean_p,
+                      double* logdet, double* quad) {
+  if (!c || !c->dTap) {
+    set_error("n2ll_taper: cocons_ctx_set_taper first");
+    return COCONS_ERR_STATE;
+  }
+  return n2ll_impl(c, COCONS_ML, theta6, limits, mean_p, logdet, quad, nullptr, nullptr, true);
+}
+
+// entry vectors of the stateless builders: rows x cols pattern, one launch
+static int taper_entries_host(const char* who, int64_t n, int64_t m, int64_t p, const double* locs,
+                              const double* locs_rows, const double* X, const double* X_rows, const double* theta6,
+                              const double* limits, const int32_t* colindices, const int32_t* rowpointers, int64_t nnz,
+                              double* out) {
+  // m == 0: square pattern over the n sites (cov_rns_taper); m > 0: m prediction rows x n columns
+  const bool square = (m == 0);
+  const int64_t nrows = square ? n : m;
+  if (n <= 0 || m < 0 || p <= 0 || !locs || !X || !theta6 || !limits || !out || (!square && (!locs_rows || !X_rows))) {
+    set_error("%s: bad argument", who);
+    return COCONS_ERR_ARG;
+  }
+  int rc = check_pattern(who, colindices, rowpointers, nrows, n, nnz);
+  if (rc) return rc;
+  if ((rc = check_device(0))) return rc;
+  double nu_fixed = 0.0;
+  // the prediction variant has no fixed-smoothness shortcut (src/cocons_taper.cpp:54-70): always the Bessel branch
+  const int mode = square ? smooth_mode_for(COCONS_PAR_DIFF, (int)p, theta6, limits, &nu_fixed) : (int)SM_GENERAL;
+  cudaStream_t st = nullptr;
+  double *dX = nullptr, *dL = nullptr, *dXr = nullptr, *dLr = nullptr, *dT = nullptr, *dS = nullptr, *dSr = nullptr,
+         *dOut = nullptr;
+  int *dCol = nullptr, *dRow = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dX), cudaFree(dL), cudaFree(dXr), cudaFree(dLr), cudaFree(dT), cudaFree(dS), cudaFree(dSr), cudaFree(dOut);
+    cudaFree(dCol), cudaFree(dRow);
+  };
+  const int64_t nz = std::max<int64_t>(nnz, 1);
+  TRY_OR_CLEAN(cudaMalloc(&dX, sizeof(double) * n * p));
+  TRY_OR_CLEAN(cudaMalloc(&dL, sizeof(double) * n * 2));
+  TRY_OR_CLEAN(cudaMalloc(&dT, sizeof(double) * 6 * p));
+  TRY_OR_CLEAN(cudaMalloc(&dS, sizeof(double) * TF_COUNT * n));
+  TRY_OR_CLEAN(cudaMalloc(&dOut, sizeof(double) * nz));
+  TRY_OR_CLEAN(cudaMalloc(&dCol, sizeof(int) * nz));
+  TRY_OR_CLEAN(cudaMalloc(&dRow, sizeof(int) * (nrows + 1)));
+  TRY_OR_CLEAN(cudaMemcpyAsync(dX, X, sizeof(double) * n * p, cudaMemcpyHostToDevice, st));
+  TRY_OR_CLEAN(cudaMemcpyAsync(dL, locs, sizeof(double) * n * 2, cudaMemcpyHostToDevice, st));
+  TRY_OR_CLEAN(cudaMemcpyAsync(dT, theta6, sizeof(double) * 6 * p, cudaMemcpyHostToDevice, st));
+  TRY_OR_CLEAN(cudaMemcpyAsync(dCol, colindices, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+  TRY_OR_CLEAN(cudaMemcpyAsync(dRow, rowpointers, sizeof(int) * (nrows + 1), cudaMemcpyHostToDevice, st));
+  TaperTable C{dS, n}, R{dS, n};
+  launch_taper_site_stage(n, (int)p, dX, n, dL, n, dT, limits[0], limits[1], mode, 0, C, st);
+  if (!square) {
+    TRY_OR_CLEAN(cudaMalloc(&dXr, sizeof(double) * m * p));
+    TRY_OR_CLEAN(cudaMalloc(&dLr, sizeof(double) * m * 2));
+    TRY_OR_CLEAN(cudaMalloc(&dSr, sizeof(double) * TF_COUNT * m));
+    TRY_OR_CLEAN(cudaMemcpyAsync(dXr, X_rows, sizeof(double) * m * p, cudaMemcpyHostToDevice, st));
+    TRY_OR_CLEAN(cudaMemcpyAsync(dLr, locs_rows, sizeof(double) * m * 2, cudaMemcpyHostToDevice, st));
+    R = TaperTable{dSr, m};
+    launch_taper_site_stage(m, (int)p, dXr, m, dLr, m, dT, limits[0], limits[1], mode, 1, R, st);
+  }
+  launch_taper_entries(0, nnz, nrows, dCol, dRow, R, C, square ? 1 : 0, mode, nu_fixed,
+                       TaperSink{TS_VECTOR, dOut, nullptr, nullptr, nullptr, 0, 0}, st);
+  TRY_OR_CLEAN(cudaGetLastError());
+  TRY_OR_CLEAN(cudaMemcpyAsync(out, dOut, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+  TRY_OR_CLEAN(cudaStreamSynchronize(st));
+  cleanup();
+  return 0;
+}
+
+int cocons_cov_rns_taper(int64_t n, int64_t p, const double* locs, const double* X, const double* theta6,
+                         const double* smooth_limits, const int32_t* colindices, const int32_t* rowpointers,
+                         int64_t nnz, double* out) {
+  return taper_entries_host("cov_rns_taper", n, 0, p, locs, nullptr, X, nullptr, theta6, smooth_limits, colindices,
+                            rowpointers, nnz, out);
+}
+
+int cocons_cov_rns_taper_pred(int64_t n, int64_t m, int64_t p, const double* locs, const double* locs_pred,
+                              const double* X, const double* X_pred, const double* theta6,
+                              const double* smooth_limits, const int32_t* colindices, const int32_t* rowpointers,
+                              int64_t nnz, double* out) {
+  if (m <= 0) {
+    set_error("cov_rns_taper_pred: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  return taper_entries_host("cov_rns_taper_pred", n, m, p, locs, locs_pred, X, X_pred, theta6, smooth_limits,
+                            colindices, rowpointers, nnz, out);
 }
 
 int cocons_profile_betas(cocons_ctx* c, int kind, double* betas) {
@@ -709,9 +870,17 @@ struct PredBlock {
   ~PredBlock() { cudaFree(dXp), cudaFree(dLp), cudaFree(dSp), cudaFree(dC); }
 };
 
+// the prediction pattern of the tapered model (pred_taper, R/predict.R:233-249): m rows x n columns
+struct TaperPred {
+  const int32_t* rowpointers = nullptr;  // host, 1-based
+  int *dCol = nullptr, *dRow = nullptr;
+  double* dTap = nullptr;
+  ~TaperPred() { cudaFree(dCol), cudaFree(dRow), cudaFree(dTap); }
+};
+
 // builds T = C L^-T for prediction sites [i0, i0+mc) into blk.dC (mp x n_pad)
 static int pred_block(cocons_ctx* c, PredBlock& blk, int64_t m, int64_t i0, int64_t mc, int64_t mp,
-                      const double* locs_pred, const double* Xp) {
+                      const double* locs_pred, const double* Xp, const TaperPred* tp) {
   const int64_t np = c->n_pad, p = c->p;
   std::vector<double> hx((size_t)mp * p, 0.0), hl((size_t)mp * 2, 0.0);
   for (int64_t k = 0; k < p; ++k)
@@ -722,12 +891,21 @@ static int pred_block(cocons_ctx* c, PredBlock& blk, int64_t m, int64_t i0, int6
   COCONS_CUDA_TRY(cudaMemcpyAsync(blk.dXp, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice, st));
   COCONS_CUDA_TRY(cudaMemcpyAsync(blk.dLp, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, st));
   COCONS_CUDA_TRY(cudaMemsetAsync(blk.dC, 0, sizeof(double) * mp * np, st));
-  SiteTable P{blk.dSp, mp, nullptr};
-  // cov_rns_pred always evaluates smoothness through the logistic (src/cocons_full.cpp:381,401)
-  const int pmode = (c->mode == SM_CLASSIC) ? SM_CLASSIC : SM_GENERAL;
-  launch_site_stage(mc, mp, (int)p, blk.dXp, mp, blk.dLp, mp, c->dTheta, c->lim[0], c->lim[1], pmode, P, st);
-  // the training table was built for cov_rns; its smooth column is only valid in general mode
-  launch_assemble_cross(mc, c->n, P, c->table(), c->global_range, blk.dC, mp, st);
+  if (tp) {
+    // taper * cov_rns_taper_pred on the rows of this block (src/cocons_taper.cpp:17-139)
+    TaperTable P{blk.dSp, mp};
+    launch_taper_site_stage(mc, (int)p, blk.dXp, mp, blk.dLp, mp, c->dTheta, c->lim[0], c->lim[1], SM_GENERAL, 1, P, st);
+    const int64_t e0 = (int64_t)tp->rowpointers[i0] - 1, e1 = (int64_t)tp->rowpointers[i0 + mc] - 1;
+    launch_taper_entries(e0, e1 - e0, m, tp->dCol, tp->dRow, P, c->taper_table(), 0, SM_GENERAL, 0.0,
+                         TaperSink{TS_ROWS, nullptr, tp->dTap, c->dInv, blk.dC, mp, i0}, st);
+  } else {
+    SiteTable P{blk.dSp, mp, nullptr};
+    // cov_rns_pred always evaluates smoothness through the logistic (src/cocons_full.cpp:381,401)
+    const int pmode = (c->mode == SM_CLASSIC) ? SM_CLASSIC : SM_GENERAL;
+    launch_site_stage(mc, mp, (int)p, blk.dXp, mp, blk.dLp, mp, c->dTheta, c->lim[0], c->lim[1], pmode, P, st);
+    // the training table was built for cov_rns; its smooth column is only valid in general mode
+    launch_assemble_cross(mc, c->n, P, c->table(), c->global_range, blk.dC, mp, st);
+  }
   COCONS_CUDA_TRY(cudaStreamSynchronize(st));  // hx/hl go out of scope
   right_solve_lt(c, blk.dC, mp);
   COCONS_CUDA_TRY(cudaGetLastError());
@@ -743,8 +921,8 @@ static int refresh_table_for_pred(cocons_ctx* c) {
   return 0;
 }
 
-int cocons_predict(cocons_ctx* c, int64_t m, const double* locs_pred, const double* Xp, const double* resid,
-                   double* stochastic, double* explained) {
+static int predict_impl(cocons_ctx* c, int64_t m, const double* locs_pred, const double* Xp, const double* resid,
+                        double* stochastic, double* explained, const TaperPred* tp) {
   if (!c || m <= 0 || !locs_pred || !Xp || !resid || !stochastic) {
     set_error("predict: bad argument");
     return COCONS_ERR_ARG;
@@ -757,9 +935,20 @@ int cocons_predict(cocons_ctx* c, int64_t m, const double* locs_pred, const doub
     set_error("predict: the kept factor uses the classic parameterisation; cocoPredict is 'diff' only");
     return COCONS_ERR_STATE;
   }
+  if (c->factor_is_taper != (tp != nullptr)) {
+    set_error(tp ? "predict_taper: the kept factor is of the dense model (call cocons_factor_taper first)"
+                 : "predict: the kept factor is of the tapered model; use cocons_predict_taper");
+    return COCONS_ERR_STATE;
+  }
   cudaSetDevice(c->device);
-  int rc = refresh_table_for_pred(c);
-  if (rc) return rc;
+  int rc = 0;
+  if (tp) {
+    // cov_rns_taper_pred always takes the smoothness through the logistic, for both site sets (:54-70)
+    launch_taper_site_stage(c->n, (int)c->p, c->dX, c->n_pad, c->dLocs, c->n_pad, c->dTheta, c->lim[0], c->lim[1],
+                            SM_GENERAL, 0, c->taper_table(), c->stream);
+  } else if ((rc = refresh_table_for_pred(c))) {
+    return rc;
+  }
   const int64_t np = c->n_pad, p = c->p;
   cudaStream_t st = c->stream;
   // y = L^-1 resid (sorted order)
@@ -782,7 +971,7 @@ int cocons_predict(cocons_ctx* c, int64_t m, const double* locs_pred, const doub
   std::vector<double> hp((size_t)2 * nsl * mc_max);
   for (int64_t i0 = 0; i0 < m; i0 += mc_max) {
     const int64_t mc = std::min<int64_t>(mc_max, m - i0), mp = mc_max;
-    if ((rc = pred_block(c, blk, m, i0, mc, mp, locs_pred, Xp))) {
+    if ((rc = pred_block(c, blk, m, i0, mc, mp, locs_pred, Xp, tp))) {
       cudaFree(dPart);
       return rc;
     }
@@ -808,6 +997,54 @@ int cocons_predict(cocons_ctx* c, int64_t m, const double* locs_pred, const doub
   }
   cudaFree(dPart);
   return 0;
+}
+
+int cocons_predict(cocons_ctx* c, int64_t m, const double* locs_pred, const double* Xp, const double* resid,
+                   double* stochastic, double* explained) {
+  return predict_impl(c, m, locs_pred, Xp, resid, stochastic, explained, nullptr);
+}
+
+int cocons_factor_taper(cocons_ctx* c, const double* theta6, const double* limits) {
+  if (!c || !theta6 || !limits) {
+    set_error("factor_taper: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  if (!c->dTap) {
+    set_error("factor_taper: cocons_ctx_set_taper first");
+    return COCONS_ERR_STATE;
+  }
+  cudaSetDevice(c->device);
+  int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, nullptr, true);
+  if (rc) return rc;
+  COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+  COCONS_CUDA_TRY(cudaMemcpyAsync(c->hInfo, c->ws.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  COCONS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  finish_timings(c);
+  if (*c->hInfo != 0) return *c->hInfo;
+  c->factor_valid = true;
+  return 0;
+}
+
+int cocons_predict_taper(cocons_ctx* c, int64_t m, const double* locs_pred, const double* Xp,
+                         const int32_t* colindices, const int32_t* rowpointers, const double* taper_entries,
+                         int64_t nnz, const double* resid, double* stochastic, double* explained) {
+  if (!c || m <= 0 || !taper_entries) {
+    set_error("predict_taper: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  int rc = check_pattern("predict_taper", colindices, rowpointers, m, c->n, nnz);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  TaperPred tp;
+  tp.rowpointers = rowpointers;
+  const int64_t nz = std::max<int64_t>(nnz, 1);
+  COCONS_CUDA_TRY(cudaMalloc(&tp.dCol, sizeof(int) * nz));
+  COCONS_CUDA_TRY(cudaMalloc(&tp.dRow, sizeof(int) * (m + 1)));
+  COCONS_CUDA_TRY(cudaMalloc(&tp.dTap, sizeof(double) * nz));
+  COCONS_CUDA_TRY(cudaMemcpy(tp.dCol, colindices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+  COCONS_CUDA_TRY(cudaMemcpy(tp.dRow, rowpointers, sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
+  COCONS_CUDA_TRY(cudaMemcpy(tp.dTap, taper_entries, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+  return predict_impl(c, m, locs_pred, Xp, resid, stochastic, explained, &tp);
 }
 
 int cocons_sim(cocons_ctx* c, int64_t k, const double* eps, double* out) {
@@ -862,6 +1099,10 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
     set_error("sim_cond: the reference's conditional branch uses the 'diff' parameterisation only");
     return COCONS_ERR_ARG;
   }
+  if (c->factor_is_taper) {
+    set_error("sim_cond: the reference's conditional branch is dense-only (R/sim.R:69-121)");
+    return COCONS_ERR_STATE;
+  }
   cudaSetDevice(c->device);
   const int64_t np = c->n_pad, p = c->p, mp = round_up(m, kTile);
   cudaStream_t st = c->stream;
@@ -884,7 +1125,7 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
     set_error("sim_cond: out of device memory");
     return COCONS_ERR_ALLOC;
   }
-  if ((rc = pred_block(c, blk, m, 0, m, mp, locs_pred, Xp))) {
+  if ((rc = pred_block(c, blk, m, 0, m, mp, locs_pred, Xp, nullptr))) {
     cleanup();
     return rc;
   }

@@ -74,6 +74,32 @@ void launch_assemble_cross(int64_t m, int64_t n, SiteTable Tpred, SiteTable Ttra
 void launch_symmetrize(int64_t n, double* C, int64_t ld, cudaStream_t st);
 void morton_order(int64_t n, const double* locs, int64_t* perm);
 
+// ---- taper.cu (sparse / tapered model, src/cocons_taper.cpp) ---------------
+enum TaperField { TF_X = 0, TF_Y, TF_R, TF_SIG, TF_NU, TF_DV, TF_COUNT };
+struct TaperTable {
+  double* base;
+  int64_t stride;
+  __host__ __device__ const double* f(int k) const { return base + (int64_t)k * stride; }
+  __host__ __device__ double* fw(int k) const { return base + (int64_t)k * stride; }
+};
+void launch_taper_site_stage(int64_t n, int p, const double* dX, int64_t ldx, const double* dlocs, int64_t ldl,
+                             const double* dtheta6, double lim0, double lim1, int mode, int pred_rows, TaperTable T,
+                             cudaStream_t st);
+enum TaperSinkKind { TS_VECTOR = 0, TS_LOWER = 1, TS_ROWS = 2 };
+struct TaperSink {
+  int kind;
+  double* out;          // TS_VECTOR: nnz values in pattern order
+  const double* taper;  // TS_LOWER / TS_ROWS: taper values on the pattern, multiplied in
+  const int* inv;       // caller index -> position in the context's ordering
+  double* A;            // dense sink
+  int64_t ld;
+  int64_t row0;         // TS_ROWS: first pattern row of the block
+};
+// entries [e0, e0 + count) of the pattern (nrows rows)
+void launch_taper_entries(int64_t e0, int64_t count, int64_t nrows, const int* dcol, const int* drow, TaperTable R,
+                          TaperTable C, int square, int mode, double nu_fixed, TaperSink S, cudaStream_t st);
+void launch_taper_pad_diag(int64_t n, int64_t n_pad, double* A, int64_t ld, cudaStream_t st);
+
 // ---- chol.cu -------------------------------------------------------------
 struct CholWorkspace {
   double* winv;               // (n_pad/kTile) inverted diagonal tiles, kTile x kTile each

@@ -22,6 +22,17 @@ cov_rns_classic <- function(theta, locs, x_covariates) {
   .Call(`_cocons_cov_rns_classic`, theta, locs, x_covariates)
 }
 
+# R/RcppExports.R:59-74 (sparse / tapered model)
+cov_rns_taper_pred <- function(theta, locs, locs_pred, x_covariates, x_covariates_pred, colindices, rowpointers,
+                               smooth_limits) {
+  .Call(`_cocons_cov_rns_taper_pred`, theta, locs, locs_pred, x_covariates, x_covariates_pred, colindices,
+        rowpointers, smooth_limits)
+}
+
+cov_rns_taper <- function(theta, locs, x_covariates, colindices, rowpointers, smooth_limits) {
+  .Call(`_cocons_cov_rns_taper`, theta, locs, x_covariates, colindices, rowpointers, smooth_limits)
+}
+
 # ---- fused objectives --------------------------------------------------------------------
 # kind: 0 ML, 1 profile, 2 REML (include/cocons_b200.h).  The device returns
 # c(status, logdet, logdet_w, rank, quad_1..quad_r); n*log(2*pi), the penalty and the `safe`
@@ -76,6 +87,43 @@ GetNeg2loglikelihoodREML <- function(theta, par.pos, locs, x_covariates, x_betas
   sum_logliks + .cocons.getPen((n - p) * dim(z)[2], lambda, theta_list, smooth.limits)
 }
 
+# ---- tapered objectives (R/neg2loglikelihood.R:20-108) -----------------------------------
+# The tapered matrix is factored densely on the device instead of by spam's sparse Cholesky, so `cholS`
+# is accepted and unused.  A context per call keeps the closures drop-in; cocoOptim's sparse branch
+# (R/optim.R:480-531) can build it once, attach the taper once and pass it through `ctx`.
+.cocons.n2ll.taper.device <- function(theta_list, ref_taper, locs, x_covariates, smooth.limits, z, ctx = NULL) {
+  tryCatch({
+    if (is.null(ctx)) {
+      ctx <- .Call(`_cocons_ctx_new`, locs, as.matrix(x_covariates), as.matrix(z), 0L)
+      on.exit(.Call(`_cocons_ctx_free`, ctx))
+      .Call(`_cocons_ctx_set_taper`, ctx, ref_taper@colindices, ref_taper@rowpointers, ref_taper@entries)
+    }
+    .Call(`_cocons_ctx_n2ll_taper`, ctx, theta_list[-1], ncol(as.matrix(x_covariates)), ncol(as.matrix(z)),
+          smooth.limits, theta_list$mean)
+  }, error = function(e) e)
+}
+
+GetNeg2loglikelihoodTaper <- function(theta, par.pos, ref_taper, locs, x_covariates, smooth.limits, cholS, z, n,
+                                      lambda, safe = TRUE, ctx = NULL) {
+  theta_list <- cocons::getModelLists(theta = theta, par.pos = par.pos, type = "diff")
+  out <- .cocons.n2ll.taper.device(theta_list, ref_taper, locs, x_covariates, smooth.limits, z, ctx)
+  if (.cocons.chol.failed(out, safe)) return(1e+06)
+  sumlogs <- sum(n * log(2 * pi) + 2 * out[2] + out[-(1:2)])
+  sumlogs + .cocons.getPen(n * dim(z)[2], lambda, theta_list, smooth.limits)
+}
+
+GetNeg2loglikelihoodTaperProfile <- function(theta, par.pos, ref_taper, locs, x_covariates, smooth.limits, cholS,
+                                             z, n, lambda, safe = TRUE, ctx = NULL) {
+  theta_list <- cocons::getModelLists(theta = theta, par.pos = par.pos, type = "diff")
+  theta_list$std.dev[1] <- 0
+  out <- .cocons.n2ll.taper.device(theta_list, ref_taper, locs, x_covariates, smooth.limits, z, ctx)
+  if (.cocons.chol.failed(out, safe)) return(1e+06)
+  r <- dim(z)[2]
+  sum_in <- sum(out[-(1:2)])
+  r * n * log(2 * pi) + r * n + r * 2 * out[2] + r * n * log(sum_in / (r * n)) +
+    .cocons.getPen(n * r, lambda, theta_list, smooth.limits)
+}
+
 # ---- factor reuse for cocoPredict / cocoSim ----------------------------------------------
 # Replace R/predict.R:136-159 by
 #   ctx  <- .Call(`_cocons_ctx_new`, coco.object@locs, X_std$std.covs, coco.object@z, 0L)
@@ -85,3 +133,12 @@ GetNeg2loglikelihoodREML <- function(theta, par.pos, locs, x_covariates, x_betas
 # and R/sim.R:162-172 by
 #   draws <- .Call(`_cocons_ctx_sim`, ctx, iiderrors)        # == t(t(iiderrors) %*% cholS)
 # with iiderrors still produced by set.seed()/rnorm() in R so that seeds reproduce.
+#
+# Sparse branches (R/predict.R:219-275, R/sim.R:193-218): with taper_two / pred_taper still holding the
+# TAPER values (before `@entries * cov_rns_taper*()`),
+#   .Call(`_cocons_ctx_set_taper`, ctx, taper_two@colindices, taper_two@rowpointers, taper_two@entries)
+#   .Call(`_cocons_ctx_factor_taper`, ctx, adjusted_eff_values[-1], ncol(X_std$std.covs), smooth.limits)
+#   pr <- .Call(`_cocons_ctx_predict_taper`, ctx, newlocs, X_pred_std$std.covs, pred_taper@colindices,
+#               pred_taper@rowpointers, pred_taper@entries, coco.resid)
+#   stochastic_part <- pr[[1]];  spam::rowSums(pred_taper * t(inv_cov)) == pr[[2]]   (:259, :274)
+# and `_cocons_ctx_sim` for the marginal draws (same distribution as t(iiderrors) %*% cholS un-permuted).

@@ -107,14 +107,43 @@ SEXP _cocons_cov_rns_classic(SEXP thetaS, SEXP locsS, SEXP xS) {
   return out;
 }
 
-/* The tapered (sparse) builders are outside this build's scope: the names
- * stay registered so the package loads; a package that keeps the sparse model links the
- * reference's own src/cocons_taper.cpp for them instead of these two stubs. */
-SEXP _cocons_cov_rns_taper_pred(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e, SEXP f, SEXP g, SEXP h) {
-  Rf_error("cov_rns_taper_pred: the sparse path is not part of cocons_b200; keep src/cocons_taper.cpp for it");
+/* spam's colindices / rowpointers slots are INTSXP; the reference's Rcpp wrappers accept any numeric
+ * vector for them (src/RcppExports.cpp:81-82, 99-100), so doubles are coerced too */
+static SEXP as_int(SEXP x) { return TYPEOF(x) == INTSXP ? x : Rf_coerceVector(x, INTSXP); }
+
+SEXP _cocons_cov_rns_taper_pred(SEXP thetaS, SEXP locsS, SEXP locsPredS, SEXP xS, SEXP xPredS, SEXP colS, SEXP rowS,
+                                SEXP limS) {
+  SEXP locs = PROTECT(as_real(locsS)), lp = PROTECT(as_real(locsPredS));
+  SEXP x = PROTECT(as_real(xS)), xp = PROTECT(as_real(xPredS)), lim = PROTECT(as_real(limS));
+  SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS));
+  const int n = Rf_nrows(locs), m = Rf_nrows(lp), p = Rf_ncols(x);
+  double* th = pack_theta(thetaS, p);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(col)));
+  int rc = (LENGTH(row) == m + 1)
+               ? cocons_cov_rns_taper_pred(n, m, p, REAL(locs), REAL(lp), REAL(x), REAL(xp), th, REAL(lim),
+                                           INTEGER(col), INTEGER(row), XLENGTH(col), REAL(out))
+               : -100;
+  free(th);
+  UNPROTECT(8);
+  if (rc == -100) Rf_error("cov_rns_taper_pred: rowpointers must have nrow(locs_pred) + 1 elements");
+  raise(rc);
+  return out;
 }
-SEXP _cocons_cov_rns_taper(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e, SEXP f) {
-  Rf_error("cov_rns_taper: the sparse path is not part of cocons_b200; keep src/cocons_taper.cpp for it");
+
+SEXP _cocons_cov_rns_taper(SEXP thetaS, SEXP locsS, SEXP xS, SEXP colS, SEXP rowS, SEXP limS) {
+  SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS)), lim = PROTECT(as_real(limS));
+  SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS));
+  const int n = Rf_nrows(locs), p = Rf_ncols(x);
+  double* th = pack_theta(thetaS, p);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(col)));
+  int rc = (LENGTH(row) == n + 1) ? cocons_cov_rns_taper(n, p, REAL(locs), REAL(x), th, REAL(lim), INTEGER(col),
+                                                         INTEGER(row), XLENGTH(col), REAL(out))
+                                  : -100;
+  free(th);
+  UNPROTECT(6);
+  if (rc == -100) Rf_error("cov_rns_taper: rowpointers must have nrow(locs) + 1 elements");
+  raise(rc);
+  return out;
 }
 
 /* ---- fused objective: what GetNeg2loglikelihood{,Profile,REML} call --------------------- */
@@ -238,6 +267,67 @@ SEXP _cocons_ctx_predict(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP residS) {
   return out;
 }
 
+/* ---- sparse (tapered) model on a resident context ----------------------------------------- */
+
+/* attach ref_taper (its colindices / rowpointers / entries slots, R/optim.R:376-379) */
+SEXP _cocons_ctx_set_taper(SEXP ptr, SEXP colS, SEXP rowS, SEXP entriesS) {
+  SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS)), ent = PROTECT(as_real(entriesS));
+  int rc = (XLENGTH(ent) == XLENGTH(col))
+               ? cocons_ctx_set_taper(ctx_of(ptr), INTEGER(col), INTEGER(row), REAL(ent), XLENGTH(col))
+               : -100;
+  UNPROTECT(3);
+  if (rc == -100) Rf_error("ctx_set_taper: entries and colindices differ in length");
+  raise(rc);
+  return R_NilValue;
+}
+
+/* c(status, logdet, quad...) of the tapered model (R/neg2loglikelihood.R:20-108) */
+SEXP _cocons_ctx_n2ll_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP rS, SEXP limS, SEXP meanS) {
+  SEXP lim = PROTECT(as_real(limS)), mean = PROTECT(as_real(meanS));
+  const int p = Rf_asInteger(pS), r = Rf_asInteger(rS);
+  double* th = pack_theta(thetaS, p);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 2 + r));
+  double logdet = R_NaReal;
+  int rc = cocons_n2ll_taper(ctx_of(ptr), th, REAL(lim), LENGTH(mean) == p ? REAL(mean) : NULL, &logdet,
+                             REAL(out) + 2);
+  free(th);
+  REAL(out)[0] = rc, REAL(out)[1] = logdet;
+  UNPROTECT(3);
+  raise(rc);
+  return out;
+}
+
+SEXP _cocons_ctx_factor_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP limS) {
+  SEXP lim = PROTECT(as_real(limS));
+  double* th = pack_theta(thetaS, Rf_asInteger(pS));
+  int rc = cocons_factor_taper(ctx_of(ptr), th, REAL(lim));
+  free(th);
+  UNPROTECT(1);
+  raise(rc);
+  return Rf_ScalarInteger(rc);
+}
+
+/* list(stochastic, explained) for the sparse cocoPredict (R/predict.R:233-275); the pattern and entries are
+ * those of pred_taper BEFORE the covariance is multiplied in */
+SEXP _cocons_ctx_predict_taper(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP colS, SEXP rowS, SEXP entriesS,
+                               SEXP residS) {
+  SEXP lp = PROTECT(as_real(locsPredS)), xp = PROTECT(as_real(xPredS)), resid = PROTECT(as_real(residS));
+  SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS)), ent = PROTECT(as_real(entriesS));
+  const int m = Rf_nrows(lp);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP sto = PROTECT(Rf_allocVector(REALSXP, m)), expl = PROTECT(Rf_allocVector(REALSXP, m));
+  int rc = (LENGTH(row) == m + 1 && XLENGTH(ent) == XLENGTH(col))
+               ? cocons_predict_taper(ctx_of(ptr), m, REAL(lp), REAL(xp), INTEGER(col), INTEGER(row), REAL(ent),
+                                      XLENGTH(col), REAL(resid), REAL(sto), REAL(expl))
+               : -100;
+  SET_VECTOR_ELT(out, 0, sto);
+  SET_VECTOR_ELT(out, 1, expl);
+  UNPROTECT(9);
+  if (rc == -100) Rf_error("ctx_predict_taper: inconsistent pattern");
+  raise(rc);
+  return out;
+}
+
 /* n x k draws L eps for cocoSim (R/sim.R:162-172); eps comes from R's own rnorm */
 SEXP _cocons_ctx_sim(SEXP ptr, SEXP epsS) {
   SEXP eps = PROTECT(as_real(epsS));
@@ -278,6 +368,10 @@ static const R_CallMethodDef CallEntries[] = {
     {"_cocons_ctx_factor", (DL_FUNC)&_cocons_ctx_factor, 5},
     {"_cocons_ctx_profile_betas", (DL_FUNC)&_cocons_ctx_profile_betas, 3},
     {"_cocons_ctx_predict", (DL_FUNC)&_cocons_ctx_predict, 4},
+    {"_cocons_ctx_set_taper", (DL_FUNC)&_cocons_ctx_set_taper, 4},
+    {"_cocons_ctx_n2ll_taper", (DL_FUNC)&_cocons_ctx_n2ll_taper, 6},
+    {"_cocons_ctx_factor_taper", (DL_FUNC)&_cocons_ctx_factor_taper, 4},
+    {"_cocons_ctx_predict_taper", (DL_FUNC)&_cocons_ctx_predict_taper, 7},
     {"_cocons_ctx_sim", (DL_FUNC)&_cocons_ctx_sim, 2},
     {"_cocons_ctx_sim_cond", (DL_FUNC)&_cocons_ctx_sim_cond, 4},
     {NULL, NULL, 0}};

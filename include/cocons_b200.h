@@ -102,6 +102,55 @@ int cocons_ctx_set_xbetas(cocons_ctx* ctx, int64_t q, const double* x_betas);
 int cocons_n2ll(cocons_ctx* ctx, int kind, const double* theta6, const double* smooth_limits, const double* mean_p,
                 double* logdet, double* quad, double* logdet_w, int* rank_x);
 
+/* ---- sparse (tapered) model, src/cocons_taper.cpp ------------------------
+ * The pattern is spam's CSR layout as the reference receives it: 1-based
+ * `colindices` (nnz) and `rowpointers` (rows + 1), INTSXP slots of the spam
+ * object (Rcpp coerces them to doubles for the reference; here they stay
+ * 32-bit integers). */
+
+/* Replaces `_cocons_cov_rns_taper` (src/RcppExports.cpp:90-104 -> cov_rns_taper,
+ * src/cocons_taper.cpp:151-433).  out: nnz covariance entries in pattern order
+ * (the caller multiplies them into the taper, R/neg2loglikelihood.R:26). */
+int cocons_cov_rns_taper(int64_t n, int64_t p, const double* locs, const double* x_covariates, const double* theta6,
+                         const double* smooth_limits, const int32_t* colindices, const int32_t* rowpointers,
+                         int64_t nnz, double* out);
+
+/* Replaces `_cocons_cov_rns_taper_pred` (src/RcppExports.cpp:71-88 -> cov_rns_taper_pred,
+ * src/cocons_taper.cpp:17-139).  The pattern has m rows (prediction sites) and n columns. */
+int cocons_cov_rns_taper_pred(int64_t n, int64_t m, int64_t p, const double* locs, const double* locs_pred,
+                              const double* x_covariates, const double* x_covariates_pred, const double* theta6,
+                              const double* smooth_limits, const int32_t* colindices, const int32_t* rowpointers,
+                              int64_t nnz, double* out);
+
+/* Attach the taper of a sparse coco object to a context: the pattern of
+ * `ref_taper` (n x n, caller order) and its entries (R/optim.R:376-379). */
+int cocons_ctx_set_taper(cocons_ctx* ctx, const int32_t* colindices, const int32_t* rowpointers,
+                         const double* taper_entries, int64_t nnz);
+
+/* GetNeg2loglikelihoodTaper / ...TaperProfile (R/neg2loglikelihood.R:20-108):
+ * taper * cov_rns_taper on the pattern -> Cholesky -> log-determinant and
+ * |R^-T (z - X mean)|^2 per column of z.  Where the reference updates spam's
+ * sparse Cholesky, the product is scattered into the dense lower triangle and
+ * factored by the same blocked DMMA Cholesky (determinant and quadratic form
+ * do not depend on spam's fill-reducing permutation).  The caller composes
+ * the value (the Profile variant sets std.dev[1] = 0 before the call, :78). */
+int cocons_n2ll_taper(cocons_ctx* ctx, const double* theta6, const double* smooth_limits, const double* mean_p,
+                      double* logdet, double* quad);
+
+/* Assemble taper * cov_rns_taper and factor it, keeping L on the device
+ * (cocoPredict / cocoSim / getCovMatrix sparse branches, R/predict.R:219-231, R/sim.R:193-204). */
+int cocons_factor_taper(cocons_ctx* ctx, const double* theta6, const double* smooth_limits);
+
+/* cocoPredict sparse branch (R/predict.R:233-275) on the factor kept by
+ * cocons_factor_taper.  The pattern (m rows x n columns) and `taper_entries`
+ * are those of `pred_taper` before its entries are multiplied by
+ * cov_rns_taper_pred - that product is formed on the device.  Outputs as
+ * cocons_predict: stochastic = resid' Sigma^-1 C' (:259),
+ * explained = rowSums(C * t(Sigma^-1 C')) (:274; NULL to skip). */
+int cocons_predict_taper(cocons_ctx* ctx, int64_t m, const double* locs_pred, const double* x_covariates_pred,
+                         const int32_t* colindices, const int32_t* rowpointers, const double* taper_entries,
+                         int64_t nnz, const double* resid, double* stochastic, double* explained);
+
 /* Profiled mean coefficients after a pml/reml fit (R/optim.R:326-343):
  * betas[q] = W^-1 V' rowSums(z) / r for the factor of the last cocons_n2ll /
  * cocons_factor call.  kind selects x_betas (PROFILE) or the full design (REML). */

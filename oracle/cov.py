@@ -2,9 +2,9 @@
 
 Two libraries, same call shapes:
   * ``restatement`` - oracle/liboracle.so, built from oracle/cov_oracle.cpp
-    (plain-array restatement of src/cocons_full.cpp:40-594);
+    (plain-array restatement of src/cocons_full.cpp:40-594 and src/cocons_taper.cpp:17-433);
   * ``reference``   - oracle/_ref/libcocons_ref.so, the reference's own
-    src/cocons_full.cpp compiled against the Rcpp/BH stand-ins (oracle/shim/).
+    src/cocons_full.cpp and src/cocons_taper.cpp compiled against the Rcpp/BH stand-ins (oracle/shim/).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import
 this module.  Matrices are numpy float64, column-major (Fortran order), as R
@@ -55,6 +55,10 @@ def _load(kind):
     f.argtypes, f.restype = [L, L, _dp, _dp, _dp, _dp], ctypes.c_int
     f = getattr(lib, prefix + "sumsmoothlone")
     f.argtypes, f.restype = [_dp, L, ctypes.c_double, ctypes.c_double], ctypes.c_double
+    f = getattr(lib, prefix + "cov_rns_taper")
+    f.argtypes, f.restype = [L, L, _dp, _dp, _dp, _dp, _dp, _dp, L, _dp], ctypes.c_int
+    f = getattr(lib, prefix + "cov_rns_taper_pred")
+    f.argtypes, f.restype = [L, L, L, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, L, _dp], ctypes.c_int
     if kind == "restatement":
         lib.oracle_bessel_k.argtypes, lib.oracle_bessel_k.restype = [ctypes.c_double, ctypes.c_double], ctypes.c_double
     _libs[kind] = (lib, prefix)
@@ -119,6 +123,37 @@ def cov_rns_classic(theta, locs, x_covariates, kind="restatement"):
     th = pack_theta(theta, p)
     out = np.empty((n, n), order="F")
     rc = getattr(lib, pre + "cov_rns_classic")(n, p, _p(locs), _p(X), _p(th), _p(out))
+    assert rc == 0
+    return out
+
+
+def cov_rns_taper(theta, locs, x_covariates, colindices, rowpointers, smooth_limits, kind="restatement"):
+    """src/cocons_taper.cpp:151-433; colindices / rowpointers are spam's 1-based CSR slots."""
+    lib, pre = _load(kind)
+    locs, X = _f(locs), _f(x_covariates)
+    n, p = X.shape
+    th, lim = pack_theta(theta, p), _f(smooth_limits)
+    ci, rp = _f(colindices), _f(rowpointers)
+    assert len(rp) == n + 1 and int(rp[-1]) - 1 == len(ci)
+    out = np.empty(len(ci))
+    rc = getattr(lib, pre + "cov_rns_taper")(n, p, _p(locs), _p(X), _p(th), _p(lim), _p(ci), _p(rp), len(ci), _p(out))
+    assert rc == 0
+    return out
+
+
+def cov_rns_taper_pred(theta, locs, locs_pred, x_covariates, x_covariates_pred, colindices, rowpointers,
+                       smooth_limits, kind="restatement"):
+    """src/cocons_taper.cpp:17-139; the pattern's rows are the prediction sites."""
+    lib, pre = _load(kind)
+    locs, lp, X, Xp = _f(locs), _f(locs_pred), _f(x_covariates), _f(x_covariates_pred)
+    n, p = X.shape
+    m = Xp.shape[0]
+    th, lim = pack_theta(theta, p), _f(smooth_limits)
+    ci, rp = _f(colindices), _f(rowpointers)
+    assert len(rp) == m + 1 and int(rp[-1]) - 1 == len(ci)
+    out = np.empty(len(ci))
+    rc = getattr(lib, pre + "cov_rns_taper_pred")(n, m, p, _p(locs), _p(lp), _p(X), _p(Xp), _p(th), _p(lim), _p(ci),
+                                                  _p(rp), len(ci), _p(out))
     assert rc == 0
     return out
 

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): CPU restatement of the reference's dense
-// covariance assembly on plain arrays.  Only tests/, __graft_entry__.smoke()
+// covariance assembly (and of the tapered one, src/cocons_taper.cpp) on plain arrays.  Only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs may load this library;
 // the product path (cocons_b200/) never does.
 //
@@ -211,6 +211,117 @@ int oracle_cov_rns_classic(long n, long p, const double* locs, const double* X, 
     }
   }
   return 0;
+}
+
+// ---- sparse (tapered) model: src/cocons_taper.cpp ---------------------------------------------
+// Isotropic nonstationary Matern on the entries of a CSR pattern (spam layout, 1-based indices
+// handed over as doubles, as Rcpp hands them to the reference).  No anisotropy / tilt here.
+struct TaperSite {
+  double range, sigma, snu;
+};
+
+// per-site stage: src/cocons_taper.cpp:54-70 (pred) and :195-209
+static void taper_site_stage(long n, long p, const double* X, const double* theta6, const double* limits,
+                             bool fill_smooth, std::vector<TaperSite>& out) {
+  const double* sd = theta6;
+  const double* scale = theta6 + p;
+  const double* smooth = theta6 + 4 * p;
+  std::vector<double> two_scale(p), half_sd(p);
+  for (long k = 0; k < p; ++k) {
+    two_scale[k] = 2 * scale[k];  // the intercept is kept (no global range in this file)
+    half_sd[k] = 0.5 * sd[k];
+  }
+  out.resize(n);
+  for (long i = 0; i < n; ++i) {
+    TaperSite s;
+    s.range = link_exp(lin_pred(X, n, p, i, two_scale.data()));
+    s.sigma = link_exp(lin_pred(X, n, p, i, half_sd.data()));
+    s.snu = 0.0;
+    if (fill_smooth)
+      s.snu = std::sqrt((limits[1] - limits[0]) / (1 + std::exp(-1 * lin_pred(X, n, p, i, smooth))) + limits[0]);
+    out[i] = s;
+  }
+}
+
+// one off-diagonal entry: src/cocons_taper.cpp:96-128 / :384-417 (path 0) and the closed forms :233-343.
+// Returns false when Q <= eps (the caller stores the row site's variance + nugget).
+static bool taper_pair(const TaperSite& a, const TaperSite& b, double dx, double dy, int path, double nu_fixed,
+                       double* v) {
+  const double nu = path ? nu_fixed : a.snu * b.snu;
+  const double prefactor = (2 * std::pow(a.range, 0.5) * std::pow(b.range, 0.5)) / (a.range + b.range);
+  const double avg = (a.range + b.range) / 2;
+  const double Q = std::sqrt(8 * nu) * std::sqrt(std::pow(dx, 2) + std::pow(dy, 2)) / std::sqrt(avg);
+  if (Q <= DBL_EPSILON) return false;
+  if (path == 1)
+    *v = prefactor * std::exp(-Q) * a.sigma * b.sigma;
+  else if (path == 2)
+    *v = prefactor * (1 + Q) * std::exp(-Q) * a.sigma * b.sigma;
+  else if (path == 3)
+    *v = prefactor * (1 + Q + Q * Q / 3) * std::exp(-Q) * a.sigma * b.sigma;
+  else if (Q < 706.0)
+    *v = prefactor * std::pow(2.0, -(nu - 1)) / std::tgamma(nu) * std::pow(Q, nu) * bessel_k(nu, Q) * a.sigma *
+         b.sigma;
+  else
+    *v = prefactor * std::pow(2.0, -(nu - 1)) / std::tgamma(nu) * std::pow(Q, nu) * std::sqrt(M_PI / (2.0 * Q)) *
+         std::exp(-Q) * a.sigma * b.sigma;
+  return true;
+}
+
+// cov_rns_taper, src/cocons_taper.cpp:151-433.  out: nnz entries in CSR order.
+int oracle_cov_rns_taper(long n, long p, const double* locs, const double* X, const double* theta6,
+                         const double* limits, const double* colindices, const double* rowpointers, long nnz,
+                         double* out) {
+  const double* sd = theta6;
+  const double* smooth = theta6 + 4 * p;
+  const double* nugget = theta6 + 5 * p;
+  bool slopes_zero = true;  // types.h:56-63
+  for (long k = 1; k < p; ++k)
+    if (smooth[k] != 0) slopes_zero = false;
+  int path = 0;
+  double nu_fixed = 0.0;
+  const bool fixed = slopes_zero && (limits[0] == limits[1]);  // :187
+  if (fixed) {
+    nu_fixed = limits[0];
+    if (std::fabs(nu_fixed - 0.5) < 1e-6) path = 1;
+    else if (std::fabs(nu_fixed - 1.5) < 1e-6) path = 2;
+    else if (std::fabs(nu_fixed - 2.5) < 1e-6) path = 3;
+  }
+  std::vector<TaperSite> S;
+  taper_site_stage(n, p, X, theta6, limits, !fixed, S);  // fixed non-half-integer nu: smooth vector stays 0
+  long e = 0;
+  for (long i = 0; i < n; ++i) {
+    for (long w = (long)(rowpointers[i] - 1); w < (long)(rowpointers[i + 1] - 1); ++w, ++e) {
+      const long j = (long)(colindices[w] - 1);
+      const double dv = link_exp(lin_pred(X, n, p, i, sd)) + link_exp(lin_pred(X, n, p, i, nugget));
+      double v;
+      if (i == j || !taper_pair(S[i], S[j], locs[i] - locs[j], locs[n + i] - locs[n + j], path, nu_fixed, &v)) v = dv;
+      out[e] = v;
+    }
+  }
+  return e == nnz ? 0 : -1;
+}
+
+// cov_rns_taper_pred, src/cocons_taper.cpp:17-139.  Rows of the pattern are prediction sites.
+int oracle_cov_rns_taper_pred(long n, long m, long p, const double* locs, const double* locs_pred, const double* X,
+                              const double* X_pred, const double* theta6, const double* limits,
+                              const double* colindices, const double* rowpointers, long nnz, double* out) {
+  const double* nugget = theta6 + 5 * p;
+  std::vector<TaperSite> S, P;
+  taper_site_stage(n, p, X, theta6, limits, true, S);
+  taper_site_stage(m, p, X_pred, theta6, limits, true, P);
+  long e = 0;
+  for (long i = 0; i < m; ++i) {
+    for (long w = (long)(rowpointers[i] - 1); w < (long)(rowpointers[i + 1] - 1); ++w, ++e) {
+      const long j = (long)(colindices[w] - 1);
+      // coincident / Q <= eps value: sigma_pred^2 + nugget (:91, :111) - sigma squared, not E(std.dev)
+      const double dv = P[i].sigma * P[i].sigma + link_exp(lin_pred(X_pred, m, p, i, nugget));
+      double v;
+      const bool same = locs_pred[i] == locs[j] && locs_pred[m + i] == locs[n + j];  // :89
+      if (same || !taper_pair(P[i], S[j], locs_pred[i] - locs[j], locs_pred[m + i] - locs[n + j], 0, 0.0, &v)) v = dv;
+      out[e] = v;
+    }
+  }
+  return e == nnz ? 0 : -1;
 }
 
 // sumsmoothlone, src/cocons_full.cpp:12-30

@@ -9,6 +9,8 @@ Outputs
                                  GPL >= 3, R/data.R:1-55) as plain float64 matrices
   tests/golden/cov_cases.npz     covariance matrices produced by the REFERENCE's own compiled
                                  source (oracle/_ref) for the inputs stored beside them
+  tests/golden/taper_cases.npz   the same for the tapered model (src/cocons_taper.cpp): entries on
+                                 nearest.dist patterns, objective and prediction values
   tests/golden/n2ll_cases.json   -2 loglik values: reference-compiled covariance + the literal
                                  numpy/LAPACK restatement of the R objectives (oracle/rmirror.py)
 """
@@ -25,7 +27,7 @@ from .rda import frame_to_matrix, read_rda
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF = "/root/reference/data"
-KIND = "reference"  # oracle/_ref: the reference's src/cocons_full.cpp compiled here
+KIND = "reference"  # oracle/_ref: the reference's src/cocons_full.cpp / cocons_taper.cpp compiled here
 
 
 def load_datasets():
@@ -142,6 +144,92 @@ def cov_cases(d):
     return out
 
 
+def taper_cases(d):
+    """Sparse (tapered) model: entries produced by the REFERENCE's own compiled src/cocons_taper.cpp on
+    brute-force nearest.dist patterns, and objective / prediction values from oracle/rmirror.py (LAPACK on the
+    dense expansion standing in for spam's sparse Cholesky)."""
+    H, HT, S = d["holes_training"], d["holes_test"], d["stripes_training"]
+    out = {}
+    n, delta = 500, 0.25
+    sc = design(H[:n], [2, 3])
+    X, locs = sc["std.covs"], H[:n, :2].copy()
+    dist, ci, rp = rmirror.nearest_dist(locs, delta=delta)
+    taper = rmirror.cov_wend1(dist, (delta, 1))
+    print("  taper pattern: n=%d nnz=%d density=%.3f" % (n, len(ci), len(ci) / n / n))
+    TH_T = dict(std_dev=[0.2, 0.15, 0.1], scale=[-2.6, 0.2, -0.15], smooth=[0.2, 0.3, -0.2], nugget=[-4, 0.1, 0.1])
+    TH_TF = dict(std_dev=[0.2, 0.15, 0.1], scale=[-2.6, 0.2, -0.15], nugget=[-4, 0.1, 0.1])
+
+    def square(name, th, lim, locs=locs, X=X, ci=ci, rp=rp):
+        out[name + "__out"] = cov.cov_rns_taper(th, locs, X, ci, rp, lim, kind=KIND)
+        for k, v in dict(theta6=cov.pack_theta(th, X.shape[1]), locs=locs, X=X, limits=lim, colindices=ci,
+                         rowpointers=rp).items():
+            out[name + "__" + k] = np.asarray(v)
+
+    square("taper_general", theta_block(3, **TH_T), [0.5, 2.5])
+    square("taper_nu05", theta_block(3, **TH_TF), [0.5, 0.5])
+    square("taper_nu15", theta_block(3, **TH_TF), [1.5, 1.5])
+    square("taper_nu25", theta_block(3, **TH_TF), [2.5, 2.5])
+    square("taper_degenerate_nu1", theta_block(3, **TH_TF), [1.0, 1.0])
+    square("taper_wide_nu", theta_block(3, **TH_T), [0.2, 4.5])
+    # tiny ranges: Q runs through the Hankel band into the >= 706 tail inside the taper radius
+    square("taper_far_pairs", theta_block(3, std_dev=[0.2, 0.15, 0.1], scale=[-9.5, 0.2, -0.15],
+                                          smooth=[0.2, 0.3, -0.2], nugget=[-4, 0.1, 0.1]), [0.5, 2.5])
+    locs_dup = locs.copy()
+    locs_dup[90], locs_dup[17] = locs_dup[5], locs_dup[100]
+    dd, cid, rpd = rmirror.nearest_dist(locs_dup, delta=delta)
+    square("taper_duplicates", theta_block(3, **TH_T), [0.5, 2.5], locs=locs_dup, ci=cid, rp=rpd)
+    ns = 331
+    scs = design(S[:ns], [2, 3, 4])
+    ds, cis, rps = rmirror.nearest_dist(S[:ns, :2], delta=0.08)
+    square("taper_stripes_p4", theta_block(4, std_dev=[0.2, 0.15, 0.1, -0.05], scale=[-2.6, 0.2, -0.15, 0.1],
+                                           smooth=[0.2, 0.3, -0.2, 0.1], nugget=[-4, 0.1, 0.1, 0.0]), [0.5, 2.5],
+           locs=S[:ns, :2], X=scs["std.covs"], ci=cis, rp=rps)
+    # prediction pattern, incl. prediction sites sitting on training sites
+    m = 90
+    lp = HT[:m, :2].copy()
+    lp[3], lp[40] = locs[10], locs[77]
+    Xp = design(HT[:m], [2, 3], sc)["std.covs"]
+    dp, cip, rpp = rmirror.nearest_dist(lp, locs, delta=delta)
+    for nm, th, lim in (("taper_pred_general", theta_block(3, **TH_T), [0.5, 2.5]),
+                        ("taper_pred_nu15", theta_block(3, **TH_TF), [1.5, 1.5])):
+        out[nm + "__out"] = cov.cov_rns_taper_pred(th, locs, lp, X, Xp, cip, rpp, lim, kind=KIND)
+        for k, v in dict(theta6=cov.pack_theta(th, 3), locs=locs, X=X, locs_pred=lp, X_pred=Xp, limits=lim,
+                         colindices=cip, rowpointers=rpp).items():
+            out[nm + "__" + k] = np.asarray(v)
+    # objectives and prediction at one theta (all-free aspects but aniso / tilt, which the tapered model ignores)
+    pp = par_pos_free(3)
+    pp["aniso"], pp["tilt"] = 0.0, 0.0
+    tl = theta_block(3, **TH_T)
+    tl["mean"] = np.array([0.1, 0.3, -0.2])
+    theta = theta_vector_from_lists(tl, pp)
+    z = np.column_stack([H[:n, 4], H[:n, 4] ** 2 - 1.0])
+    out["obj__theta"], out["obj__z"], out["obj__delta"] = theta, z, np.array(delta)
+    out["obj__ml"] = np.array(rmirror.neg2loglik_taper(theta, pp, taper, ci, rp, locs, X, [0.5, 2.5], z, n,
+                                                       (0.0, 0.0, 0.0), cov_kind=KIND))
+    out["obj__ml_pen"] = np.array(rmirror.neg2loglik_taper(theta, pp, taper, ci, rp, locs, X, [0.5, 2.5], z, n,
+                                                           (0.05, 0.02, 0.3), cov_kind=KIND))
+    ppp = dict(pp)
+    ppp["std.dev"] = np.array([False, True, True])
+    theta_p = np.delete(theta, 3)  # drop the std.dev intercept slot (R/optim.R:570-576)
+    out["obj__theta_profile"] = theta_p
+    out["obj__profile"] = np.array(rmirror.neg2loglik_taper_profile(theta_p, ppp, taper, ci, rp, locs, X, [0.5, 2.5],
+                                                                    z, n, (0.0, 0.0, 0.0), cov_kind=KIND))
+    back = rmirror.get_model_lists(theta, pp, "diff")
+    pr = rmirror.predict_taper(back, delta, locs, lp, X, Xp, [0.5, 2.5], z[:, 0], "pred", cov_kind=KIND)
+    out["obj__pred_stochastic"], out["obj__pred_sd"] = pr["stochastic"], pr["sd.pred"]
+    # not positive definite: a pattern whose row 8 lost its diagonal entry (zero pivot) -> 1e6 under safe = TRUE
+    k = int(rp[7] - 1 + np.flatnonzero(ci[rp[7] - 1:rp[8] - 1] == 8)[0])
+    ci_bad, taper_bad = np.delete(ci, k), np.delete(taper, k)
+    rp_bad = rp.copy()
+    rp_bad[8:] -= 1
+    out["obj__notpd_colindices"], out["obj__notpd_rowpointers"], out["obj__notpd_taper"] = ci_bad, rp_bad, taper_bad
+    out["obj__notpd"] = np.array(rmirror.neg2loglik_taper(theta, pp, taper_bad, ci_bad, rp_bad, locs, X, [0.5, 2.5], z,
+                                                          n, (0.0, 0.0, 0.0), cov_kind=KIND))
+    print("  taper objectives: ml %.10f  profile %.10f  notpd %g" % (out["obj__ml"], out["obj__profile"],
+                                                                    out["obj__notpd"]))
+    return out
+
+
 def par_pos_free(p, mean_free=True):
     pp = {k: np.ones(p, dtype=bool) for k in rmirror.ASPECT_ORDER}
     if not mean_free:
@@ -235,7 +323,7 @@ def n2ll_cases(d, quick):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", choices=["datasets", "cov", "n2ll"], default=None)
+    ap.add_argument("--only", choices=["datasets", "cov", "n2ll", "taper"], default=None)
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     cov.build(force=True)
@@ -244,6 +332,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "datasets.npz"), **d)
     if args.only in (None, "cov"):
         np.savez_compressed(os.path.join(GOLD, "cov_cases.npz"), **cov_cases(d))
+    if args.only in (None, "taper"):
+        np.savez_compressed(os.path.join(GOLD, "taper_cases.npz"), **taper_cases(d))
     if args.only in (None, "n2ll"):
         cases = n2ll_cases(d, args.quick)
         with open(os.path.join(GOLD, "n2ll_cases.json"), "w") as f:

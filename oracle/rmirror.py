@@ -257,3 +257,116 @@ def sim_conditional(theta_list, locs, newlocs, X_std, X_pred_std, smooth_limits,
     mu = pr["systematic"] + pr["stochastic"]
     eps = np.asarray(eps, dtype=np.float64).reshape(C.shape[0], -1)
     return (eps.T @ L + mu[None, :]).T
+
+
+# ---- sparse (tapered) model ---------------------------------------------------------------
+# spam (>= 2.9.1, DESCRIPTION:21) is third-party and absent: its sparse matrices are (entries,
+# colindices, rowpointers) triples here, nearest.dist is a brute-force distance threshold, cov.wend1
+# is its documented formula, and its sparse Cholesky / solve are replaced by LAPACK on the dense
+# expansion - determinant, quadratic forms and solutions do not depend on spam's fill-reducing
+# permutation, so the values are those of the reference up to rounding.
+def nearest_dist(x, y=None, delta=1.0):
+    """spam::nearest.dist(..., upper = NULL): Euclidean distances <= delta, zero distances and the diagonal kept.
+    Returns (distances, colindices, rowpointers), 1-based CSR with ascending columns."""
+    x = np.asarray(x, dtype=np.float64)
+    y = x if y is None else np.asarray(y, dtype=np.float64)
+    ent, ci, rp = [], [], [1]
+    for i in range(x.shape[0]):
+        d = np.sqrt((x[i, 0] - y[:, 0]) ** 2 + (x[i, 1] - y[:, 1]) ** 2)
+        j = np.flatnonzero(d <= delta)
+        ent.append(d[j]), ci.append(j + 1)
+        rp.append(rp[-1] + len(j))
+    return np.concatenate(ent), np.concatenate(ci), np.asarray(rp)
+
+
+def cov_wend1(h, theta):
+    """spam::cov.wend1(h, theta = c(range, sill)): sill (1 - d)^4_+ (1 + 4 d), d = h / range."""
+    d = np.asarray(h, dtype=np.float64) / theta[0]
+    return theta[1] * np.where(d < 1, (1 - d) ** 4 * (1 + 4 * d), 0.0)
+
+
+def csr_to_dense(entries, colindices, rowpointers, ncol):
+    nrow = len(rowpointers) - 1
+    out = np.zeros((nrow, ncol))
+    rows = np.repeat(np.arange(nrow), np.diff(rowpointers))
+    out[rows, np.asarray(colindices, dtype=np.int64) - 1] = entries
+    return out
+
+
+def tapered_matrix(theta_list, taper, colindices, rowpointers, locs, x_covariates, smooth_limits,
+                   cov_kind="restatement"):
+    """ref_taper@entries * cov_rns_taper(...) (R/neg2loglikelihood.R:26-31), expanded to a dense n x n matrix.
+    spam's Cholesky reads one triangle of the (ulp-level asymmetric) matrix; the lower one is used here."""
+    ent = taper * _cov.cov_rns_taper(theta_list, locs, x_covariates, colindices, rowpointers, smooth_limits,
+                                     kind=cov_kind)
+    S = np.tril(csr_to_dense(ent, colindices, rowpointers, len(rowpointers) - 1))
+    return S + np.tril(S, -1).T
+
+
+def _taper_chol_terms(tl, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, z, n, cov_kind):
+    S = tapered_matrix(tl, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, cov_kind)
+    R = r_chol(S)
+    logdet = np.sum(np.log(np.diag(R)))  # determinant.spam.chol.NgPeyton(cholS)$modulus
+    trend = np.asarray(x_covariates) @ tl["mean"]
+    z = np.asarray(z, dtype=np.float64).reshape(n, -1)
+    quads = []
+    for c in range(z.shape[1]):
+        y = _fwd(R, z[:, c] - trend)
+        quads.append(float(y @ y))
+    return logdet, quads
+
+
+def neg2loglik_taper(theta, par_pos, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, z, n, lam,
+                     safe=True, cov_kind="restatement"):
+    """GetNeg2loglikelihoodTaper, R/neg2loglikelihood.R:20-53."""
+    tl = get_model_lists(theta, par_pos, "diff")
+    try:
+        logdet, quads = _taper_chol_terms(tl, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, z,
+                                          n, cov_kind)
+    except CholeskyError:
+        if safe:
+            return 1e6
+        raise CholeskyError("Cholesky error")
+    total = sum(n * np.log(2 * np.pi) + 2 * logdet + q for q in quads)
+    return total + get_pen(n * len(quads), lam, tl, smooth_limits)
+
+
+def neg2loglik_taper_profile(theta, par_pos, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, z,
+                             n, lam, safe=True, cov_kind="restatement"):
+    """GetNeg2loglikelihoodTaperProfile, R/neg2loglikelihood.R:73-108."""
+    tl = get_model_lists(theta, par_pos, "diff")
+    tl["std.dev"][0] = 0.0  # :78
+    try:
+        logdet, quads = _taper_chol_terms(tl, taper, colindices, rowpointers, locs, x_covariates, smooth_limits, z,
+                                          n, cov_kind)
+    except CholeskyError:
+        if safe:
+            return 1e6
+        raise CholeskyError("Cholesky error")
+    r = len(quads)
+    sum_in = float(np.sum(quads))
+    return (r * n * np.log(2 * np.pi) + r * n + r * 2 * logdet + r * n * np.log(sum_in / (r * n)) +
+            get_pen(n * r, lam, tl, smooth_limits))
+
+
+def predict_taper(theta_list, delta, locs, newlocs, X_std, X_pred_std, smooth_limits, z_col, type="mean",
+                  taper_fn=cov_wend1, cov_kind="restatement"):
+    """cocoPredict sparse branch, R/predict.R:219-288."""
+    n, m = len(locs), len(newlocs)
+    d, ci, rp = nearest_dist(locs, delta=delta)
+    S = tapered_matrix(theta_list, taper_fn(d, (delta, 1)), ci, rp, locs, X_std, smooth_limits, cov_kind)
+    dp, cip, rpp = nearest_dist(newlocs, locs, delta=delta)
+    ent = taper_fn(dp, (delta, 1)) * _cov.cov_rns_taper_pred(theta_list, locs, newlocs, X_std, X_pred_std, cip, rpp,
+                                                             smooth_limits, kind=cov_kind)
+    C = csr_to_dense(ent, cip, rpp, n)
+    inv_cov = np.linalg.solve(S, C.T)
+    systematic = X_pred_std @ theta_list["mean"]
+    resid = np.asarray(z_col, dtype=np.float64) - X_std @ theta_list["mean"]
+    out = {"systematic": systematic, "stochastic": resid @ inv_cov}
+    if type == "pred":
+        u = 1 / np.exp(-(X_pred_std @ theta_list["std.dev"])) + np.exp(X_pred_std @ theta_list["nugget"])
+        u = u - np.sum(C * inv_cov.T, axis=1)
+        neg = u < 1e-10
+        u[neg] = np.abs(u[neg])
+        out["sd.pred"] = np.sqrt(u)
+    return out

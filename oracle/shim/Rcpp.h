@@ -3,7 +3,7 @@
 // Rcpp is not installed in this image, so the reference's
 // src/cocons_full.cpp cannot be compiled against the real headers.  This
 // header supplies just enough of the Rcpp container surface that
-// /root/reference/src/cocons_full.cpp + cocons_types.h compile UNMODIFIED,
+// /root/reference/src/cocons_full.cpp, cocons_taper.cpp + cocons_types.h compile UNMODIFIED,
 // from where they lie, into oracle/_ref/ (see oracle/Makefile).  Semantics
 // mirrored: NumericVector/NumericMatrix are reference-counted handles
 // (copy = alias, clone() = deep copy), matrices are column-major and
@@ -95,6 +95,13 @@ inline NumericVector operator*(int s, const NumericVector& v) { return (double)s
 inline NumericVector operator+(const NumericVector& a, const NumericVector& b) {
   NumericVector out(a.size());
   for (long k = 0; k < a.size(); ++k) out[k] = a[k] + b[k];
+  return out;
+}
+
+// `colindices - 1` (src/cocons_taper.cpp:76-77, 213-214): element-wise, fresh storage
+inline NumericVector operator-(const NumericVector& a, int s) {
+  NumericVector out(a.size());
+  for (long k = 0; k < a.size(); ++k) out[k] = a[k] - s;
   return out;
 }
 

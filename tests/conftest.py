@@ -31,6 +31,16 @@ def cov_cases():
 
 
 @pytest.fixture(scope="session")
+def taper_cases():
+    raw = np.load(os.path.join(GOLD, "taper_cases.npz"), allow_pickle=False)
+    cases = {}
+    for key in raw.files:
+        name, field = key.split("__")
+        cases.setdefault(name, {})[field] = raw[key]
+    return cases
+
+
+@pytest.fixture(scope="session")
 def n2ll_cases():
     with open(os.path.join(GOLD, "n2ll_cases.json")) as f:
         doc = json.load(f)
