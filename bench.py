@@ -302,10 +302,12 @@ def run_ours(args, rank, world, local_rank):
     f_ms = float(np.mean(phases["factor_ms"]))
     phase_tflops = flops_chol(n) / (f_ms * 1e-3) / 1e12
     # dominant kernel: the largest trailing-update launch of each factorisation (C -= P P^T on the
-    # (n_pad - 1024)^2 lower triangle, K = 512), bracketed by CUDA events inside the timed region
+    # (n_pad - 2K)^2 lower triangle, K = 768 at n = 50 000), bracketed by CUDA events inside the timed region
     n_pad = (n + 127) // 128 * 128
-    rest = n_pad - 1024
-    kernel_flops = rest * (rest + 1) / 2 * 2 * 512  # algorithmic: lower triangle incl. diagonal
+    # outer panel width, the rule of chol_outer() in csrc/chol.cu: 768 from 16 384 sites up, else 512
+    kk = 128 * max(1, min(int(os.environ.get("COCONS_CHOL_OUTER", "6" if n_pad >= 16384 else "4")), 16))
+    rest = n_pad - 2 * kk
+    kernel_flops = rest * (rest + 1) / 2 * 2 * kk  # algorithmic: lower triangle incl. diagonal
     k_ms = float(np.mean(phases["kernel_ms"]))
     achieved = kernel_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
     traffic, traffic_src = None, None
@@ -329,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
         "assembly_pairs_per_s": n * (n - 1) / 2 / (float(np.mean(phases["assembly_ms"])) * 1e-3),
         "roofline": {"bound": "tensor",
                      "kernel": "gemm_nt_tma_kernel<64,2,0> (DMMA.8x8x4 trailing update, bulk-copy fed): the largest "
-                               "launch of each factorisation, %d^2 lower triangle x K=512" % rest,
+                               "launch of each factorisation, %d^2 lower triangle x K=%d" % (rest, kk),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if (peak and achieved) else None,
                      "traffic": traffic, "traffic_source": traffic_src,

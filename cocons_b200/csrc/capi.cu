@@ -520,13 +520,14 @@ static int finish_timings(cocons_ctx* c) {
   COCONS_CUDA_TRY(cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
   c->ms[0] = a, c->ms[1] = b, c->ms[2] = d, c->ms[3] = a + b + d;
   c->kernel_ms = 0, c->kernel_flops = 0;
-  const int64_t rest = c->n_pad - 8 * kTile;  // rows/cols right of the first two 512-wide panels
+  const int64_t outer = chol_outer(c->n_pad);
+  const int64_t rest = c->n_pad - 2 * outer * kTile;  // rows/cols right of the first two outer panels
   if (rest > 0) {
     float km = 0;
     if (cudaEventElapsedTime(&km, c->ws.ev_k0, c->ws.ev_k1) == cudaSuccess) {
       const double tiles = 2.0 * ((double)(rest / kTile) * (rest / kTile + 1) / 2.0);  // 128 x 64 tiles computed
       c->kernel_ms = km;
-      c->kernel_flops = tiles * 2.0 * 128.0 * 64.0 * 512.0;
+      c->kernel_flops = tiles * 2.0 * 128.0 * 64.0 * (double)(outer * kTile);
     }
   }
   return 0;

@@ -9,7 +9,7 @@
 //                       the bulk-copy (TMA) engine onto mbarriers; used for the panel
 //                       solve (X = A inv(L_jj)^T), the in-panel update and the
 //                       trailing SYRK update
-//   chol_factor         two-level driver: 128-wide steps inside 512-wide panels
+//   chol_factor         two-level driver: 128-wide steps inside 512- or 768-wide panels
 #include <algorithm>
 #include <type_traits>
 
@@ -587,10 +587,24 @@ void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws,
 // Look-ahead: the update by panel J is split into (a) the columns of panel J+1 and (b) everything
 // to their right.  As soon as (a) is done, panel J+1 is factored on a high-priority side stream
 // while (b) - where the flops are - keeps the SMs busy on the main stream.
+// tiles per outer panel: trailing updates run with K = 128 * chol_outer(n_pad).  Measured on B200 at
+// n = 50 000: K = 512 -> 1209.7 ms, 768 -> 1200.1, 1024 -> 1199.6 (the read-modify-write epilogue of C is
+// amortised over a longer K; standalone SYRK 35.19 / 35.50 / 35.65 TFLOP/s); below ~16 k sites the longer
+// panel chain costs more than it saves.  COCONS_CHOL_OUTER overrides.
+int chol_outer(int64_t n_pad) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("COCONS_CHOL_OUTER");
+    forced = e ? std::max(1, std::min(atoi(e), 16)) : 0;
+  }
+  if (forced > 0) return forced;
+  return n_pad >= 16384 ? 6 : 4;
+}
+
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st) {
   cudaMemsetAsync(ws.info, 0, sizeof(int), st);
   const int64_t nt = n_pad / kTile;
-  const int64_t outer = 4;
+  const int64_t outer = chol_outer(n_pad);
   factor_panel(A, n_pad, ld, ws, 0, std::min<int64_t>(outer, nt), st);
   for (int64_t J0 = 0; J0 < nt; J0 += outer) {
     const int64_t jb = std::min<int64_t>(outer, nt - J0);

@@ -115,6 +115,7 @@ void chol_workspace_destroy(CholWorkspace* ws);
 void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws, int64_t J0, int64_t jb,
                   cudaStream_t st);
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st);
+int chol_outer(int64_t n_pad);  // tiles per outer panel of chol_factor
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st);
 
