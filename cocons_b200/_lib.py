@@ -35,6 +35,7 @@ SIGNATURES = {
     "cocons_cov_rns_pred": (ctypes.c_int, [_i64, _i64, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "cocons_cov_rns_classic": (ctypes.c_int, [_i64, _i64, _dp, _dp, _dp, _dp]),
     "cocons_sumsmoothlone": (ctypes.c_double, [_dp, _i64, ctypes.c_double, ctypes.c_double]),
+    "cocons_qr_rank": (ctypes.c_int, [_dp, _i64, _i64, ctypes.c_double]),
     "cocons_ctx_create": (ctypes.c_int, [ctypes.c_int, _i64, _i64, _i64, _dp, _dp, _dp, _vp, ctypes.POINTER(_vp)]),
     "cocons_ctx_destroy": (None, [_vp]),
     "cocons_ctx_set_z": (ctypes.c_int, [_vp, _dp]),

@@ -240,6 +240,12 @@ static int check_device(int device) {
   return 0;
 }
 
+// device of the stateless / one-shot entry points: COCONS_DEVICE (one R worker per GPU sets it), default 0
+static int default_device() {
+  const char* env = getenv("COCONS_DEVICE");
+  return env ? atoi(env) : 0;
+}
+
 // upload a caller-order n x k column-major host matrix into a sorted, zero-padded n_pad x k device matrix
 static int upload_sorted(cocons_ctx* c, const double* src, int64_t k, double* dst) {
   std::vector<double> tmp((size_t)c->n_pad * k, 0.0);
@@ -259,6 +265,14 @@ int cocons_device_count(void) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
   return count;
+}
+
+int cocons_qr_rank(const double* X, int64_t n, int64_t p, double tol) {
+  if (!X || n <= 0 || p <= 0 || p > 4096) {
+    set_error("qr_rank: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  return qr_rank_dqrdc2(X, n, (int)p, tol);
 }
 
 double cocons_sumsmoothlone(const double* x, int64_t len, double lambda, double alpha) {
@@ -281,7 +295,7 @@ static int cov_square(int par, int64_t n, int64_t p, const double* locs, const d
     set_error("cov_rns: bad argument");
     return COCONS_ERR_ARG;
   }
-  int rc = check_device(0);
+  int rc = check_device(default_device());
   if (rc) return rc;
   const double lim[2] = {limits ? limits[0] : 0.0, limits ? limits[1] : 0.0};
   double nu_fixed;
@@ -340,7 +354,7 @@ int cocons_cov_rns_pred(int64_t n, int64_t m, int64_t p, const double* locs, con
     set_error("cov_rns_pred: bad argument");
     return COCONS_ERR_ARG;
   }
-  int rc = check_device(0);
+  int rc = check_device(default_device());
   if (rc) return rc;
   const double global_range = 1 / std::exp(-2 * theta6[p]);  // :351
   cudaStream_t st = nullptr;
@@ -703,7 +717,7 @@ static int taper_entries_host(const char* who, int64_t n, int64_t m, int64_t p, 
   }
   int rc = check_pattern(who, colindices, rowpointers, nrows, n, nnz);
   if (rc) return rc;
-  if ((rc = check_device(0))) return rc;
+  if ((rc = check_device(default_device()))) return rc;
   double nu_fixed = 0.0;
   // the prediction variant has no fixed-smoothness shortcut (src/cocons_taper.cpp:54-70): always the Bessel branch
   const int mode = square ? smooth_mode_for(COCONS_PAR_DIFF, (int)p, theta6, limits, &nu_fixed) : (int)SM_GENERAL;
@@ -1205,8 +1219,7 @@ int cocons_neg2loglik_dense(int kind, int64_t n, int64_t p, int64_t r, int64_t q
                             const double* z, const double* xb, const double* theta6, const double* limits,
                             const double* mean_p, double* logdet, double* quad, double* logdet_w, int* rank_x) {
   std::lock_guard<std::mutex> lock(g_ws_mutex);
-  int device = 0;
-  if (const char* env = getenv("COCONS_DEVICE")) device = atoi(env);
+  const int device = default_device();
   int rc;
   if (g_ws && (g_ws->n != n || g_ws->p != p || g_ws->r != r || g_ws->device != device)) {
     cocons_ctx_destroy(g_ws);

@@ -315,6 +315,7 @@ def _terms_from_gram(kind, logdet, G, qx, r, X):
         t = np.linalg.solve(Lw, G[:qx, qx + j])
         quad[j] = G[qx + j, qx + j] - t @ t
     out["quad"] = quad
-    if kind == _lib.REML:
-        out["rank"] = int(np.linalg.matrix_rank(X, tol=None))
+    if kind == _lib.REML:  # qr(X)$rank, R/neg2loglikelihood.R:270 - the same routine the single-GPU path uses
+        Xf = _lib.fmat(X)
+        out["rank"] = int(_lib.lib().cocons_qr_rank(_lib.ptr(Xf), Xf.shape[0], Xf.shape[1], 1e-7))
     return out

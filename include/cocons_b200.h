@@ -13,7 +13,8 @@
  * CUDA/NCCL/argument error, text in cocons_last_error().
  *
  * There is no CPU fallback: every entry point that computes fails with
- * COCONS_ERR_NO_DEVICE when no sm_100 device is usable.
+ * COCONS_ERR_NO_DEVICE when no sm_100 device is usable.  The stateless and
+ * one-shot entry points run on device $COCONS_DEVICE (default 0).
  */
 #ifndef COCONS_B200_H
 #define COCONS_B200_H
@@ -69,6 +70,10 @@ int cocons_cov_rns_classic(int64_t n, int64_t p, const double* locs, const doubl
 /* Replaces `_cocons_sumsmoothlone` (src/RcppExports.cpp:16-26 -> sumsmoothlone,
  * src/cocons_full.cpp:12-30).  A p-length host reduction; stays on the host. */
 double cocons_sumsmoothlone(const double* x, int64_t len, double lambda, double alpha);
+
+/* qr(X)$rank as base R computes it (LINPACK dqrdc2 with limited column pivoting, tol = 1e-7), which
+ * GetNeg2loglikelihoodREML evaluates at R/neg2loglikelihood.R:270.  X is n x p column-major.  Host code. */
+int cocons_qr_rank(const double* x, int64_t n, int64_t p, double tol);
 
 /* ---- likelihood context: theta-independent inputs resident on the device -
  *
