@@ -27,6 +27,7 @@ from .api import (  # noqa: F401
     cov_wend2,
     fd_value_and_grad,
     getCovMatrix,
+    getDensityFromDelta,
     getDesignMatrix,
     getHessian,
     getModelLists,

@@ -606,6 +606,14 @@ def getCovMatrix(coco_object):
     return cov_rns(theta_list, coco_object.locs, x_covs, coco_object.info["smooth.limits"])
 
 
+def getDensityFromDelta(coco_object, delta):
+    """R/getFunctions.R:133-146: density of the tapered covariance matrix for a taper range `delta` (the
+    fraction of stored entries, which depends on the pattern only)."""
+    if coco_object.type != "sparse":
+        raise ValueError("only for sparse coco objects.")
+    return nearest_dist(coco_object.locs, delta=delta).density()
+
+
 def _ref_taper(coco_object, rows=None):
     """info$taper(spam::nearest.dist(locs, delta = info$delta, upper = NULL), theta = c(delta, 1)),
     R/optim.R:376-379; with `rows`, the prediction pattern of R/predict.R:233-235."""
@@ -658,7 +666,7 @@ def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None,
 
 def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml", optim_control=None, device=0,
               forward=False):
-    """R/optim.R:65-365, dense branch.  L-BFGS-B (scipy) stands in for optimParallel's optimiser; its
+    """R/optim.R:65-365 (dense) and :366-690 (sparse, see _cocoOptim_sparse).  L-BFGS-B (scipy) stands in for optimParallel's optimiser; its
     gradient is the same batched finite-difference scheme (fd_value_and_grad), whose independent
     objective evaluations run on the device-resident context of each rank - across all GPUs when
     launched with one process per GPU - instead of on forked R workers.
@@ -683,6 +691,10 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     par_pos = dm["par.pos"]
     z = coco_object.z
     x_betas = None
+    if coco_object.type == "sparse":
+        nc = max(1, min(8, int(4e9 // (8 * n * n)))) if ncores == "auto" else int(ncores)
+        return _cocoOptim_sparse(coco_object, boundaries, dm, sc, mod_DM, init, lower, upper, ctrl, ndeps, forward,
+                                 nc, safe, optim_type, device)
     if optim_type in ("pml", "reml"):
         if not isinstance(par_pos["mean"], np.ndarray):
             raise ValueError("Profile ML or Restricted ML only available when considering covariates in the mean.")
@@ -697,9 +709,6 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     # contexts on one GPU; "auto" = as many as fit comfortably, none extra once one evaluation fills the GPU
     if ncores == "auto":
         ncores = max(1, min(8, int(4e9 // (8 * n * n))))
-    if coco_object.type == "sparse":
-        return _cocoOptim_sparse(coco_object, boundaries, dm, sc, mod_DM, init, lower, upper, ctrl, ndeps, forward,
-                                 int(ncores), safe, optim_type, device)
     with DenseLikelihoodPool(coco_object.locs, mod_DM, z, size=int(ncores), device=device) as pool:
         ctx = pool.ctxs[0]
         if optim_type == "pml":

@@ -217,3 +217,44 @@ def test_diagonal_pattern_at_scale():
     resid = z.reshape(-1) - X @ tl["mean"]
     assert abs(t["logdet"] - 0.5 * np.sum(np.log(dv))) < 1e-11 * abs(0.5 * np.sum(np.log(dv)))
     assert abs(t["quad"][0] - np.sum(resid ** 2 / dv)) < 1e-11 * np.sum(resid ** 2 / dv)
+
+
+def test_sparse_smoke_sequence_of_the_reference_test_script(datasets):
+    """tests/coco_test.R:130-200 in miniature: sparse coco object (nu = 1.5, Wendland-1 taper), "ml" and "pml"
+    fits, the tapered covariance matrix is positive definite, predictions hold no NaN; plus the identity
+    that ties the pml recovery (R/optim.R:590-662) together: at the recovered parameters the full tapered
+    objective equals the profiled one at the optimum."""
+    H, T = datasets["holes_training"][:100], datasets["holes_test"][:60]
+    data = {"x": H[:, 0], "y": H[:, 1], "cov_x": H[:, 2], "cov_y": H[:, 3]}
+    ml = {"mean": 0, "std.dev": "~ 1 + cov_x", "scale": "~ 1", "aniso": 0, "tilt": 0, "smooth": 1.5,
+          "nugget": -np.inf}
+    info = {"taper": cb.cov_wend1, "delta": 0.4}
+    obj = cb.coco("sparse", data, H[:, :2], H[:, 4], ml, info=dict(info))
+    assert 0 < cb.getDensityFromDelta(obj, 0.2) < cb.getDensityFromDelta(obj, 0.4) < 1
+    with pytest.raises(ValueError, match="only for sparse"):
+        cb.getDensityFromDelta(cb.coco("dense", data, H[:, :2], H[:, 4], ml), 0.2)
+    bounds = {"theta_init": np.array([0.0, 0.0, -1.0]), "theta_lower": np.array([-4.0, -2.0, -6.0]),
+              "theta_upper": np.array([4.0, 2.0, 4.0])}
+    fit = cb.cocoOptim(obj, bounds, optim_control={"maxiter": 25})
+    assert fit.output["value"] < 1e6 and np.all(np.isfinite(fit.output["par"]))
+    cmat = cb.getCovMatrix(fit).toarray()
+    cmat = np.tril(cmat) + np.tril(cmat, -1).T
+    assert cmat.shape == (100, 100) and np.all(np.linalg.eigvalsh(cmat) > 0)
+    newdata = {"x": T[:, 0], "y": T[:, 1], "cov_x": T[:, 2], "cov_y": T[:, 3]}
+    pr = cb.cocoPredict(fit, newdata, T[:, :2], type="pred")
+    assert not np.any(np.isnan(pr["stochastic"])) and np.all(pr["sd.pred"] > 0)
+    # the fit did not end above its starting value
+    dm = cb.getDesignMatrix(obj.model_list, obj.data)
+    X = cb.getScale(dm["model.matrix"])["std.covs"]
+    ref_taper = cb.cov_wend1(cb.nearest_dist(H[:, :2], delta=0.4), (0.4, 1))
+    f0 = cb.GetNeg2loglikelihoodTaper(bounds["theta_init"], dm["par.pos"], ref_taper, H[:, :2], X, [1.5, 1.5], None,
+                                      H[:, 4], 100, (0, 0, 0))
+    assert fit.output["value"] <= f0 + 1e-9 * abs(f0)
+    # pml: the global variance is profiled out and recovered
+    obj2 = cb.coco("sparse", data, H[:, :2], H[:, 4], ml, info=dict(info))
+    fit2 = cb.cocoOptim(obj2, bounds, optim_type="pml", optim_control={"maxiter": 25})
+    assert fit2.output["par"].shape == (3,) and np.all(np.isfinite(fit2.output["par"]))
+    full = cb.GetNeg2loglikelihoodTaper(fit2.output["par"], dm["par.pos"], ref_taper, H[:, :2], X, [1.5, 1.5], None,
+                                        H[:, 4], 100, (0, 0, 0))
+    assert abs(full - fit2.output["value"]) < 1e-8 * abs(full), (full, fit2.output["value"])
+    assert fit2.output["value"] <= fit.output["value"] + 1e-6 * abs(fit.output["value"])
