@@ -55,6 +55,7 @@ SIGNATURES = {
     "cocons_sim_cond": (ctypes.c_int, [_vp, _i64, _dp, _dp, _i64, _dp, _dp]),
     "cocons_ctx_get_factor": (ctypes.c_int, [_vp, _dp, _lp]),
     "cocons_ctx_timings": (ctypes.c_int, [_vp, _dp]),
+    "cocons_ctx_debug_checksums": (ctypes.c_int, [_vp, _dp]),
     "cocons_ctx_kernel_timing": (ctypes.c_int, [_vp, _dp, _dp]),
     "cocons_neg2loglik_dense": (ctypes.c_int, [ctypes.c_int, _i64, _i64, _i64, _i64, _dp, _dp, _dp, _dp, _dp, _dp,
                                                _dp, _dp, _dp, _dp, _ip]),

@@ -922,9 +922,11 @@ def cocoSim(coco_object, pars=None, n=1, seed=None, standardize=True, type="clas
 # --------------------------------------------------------------------------
 class DenseLikelihoodPool:
     """`size` device-resident contexts over the same data, each with its own streams, driven by host
-    threads (the C ABI releases the GIL).  Below n ~ 10 000 one evaluation is a latency-bound chain of
-    small kernels that leaves most of the 148 SMs idle; running the optimiser's independent
-    finite-difference points (R/optim.R:157,256,321) side by side fills them."""
+    threads (the C ABI releases the GIL): the shape of the optimiser's independent finite-difference points
+    (R/optim.R:157,256,321).  The library runs ONE evaluation at a time per device: overlapping the kernel
+    chains of several contexts was measurably faster below n ~ 10 000 but not reproducible
+    (profiles/r01_reference_datasets_pool.md), so on one GPU the pool only overlaps host work with device work;
+    the speed-up across GPUs comes from distributed.fan_out."""
 
     def __init__(self, locs, x_covariates, z, size=4, device=0):
         from concurrent.futures import ThreadPoolExecutor

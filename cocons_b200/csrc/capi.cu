@@ -182,6 +182,27 @@ using namespace cocons;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+// debugging aid (COCONS_DEBUG_CHECKSUM=1): deterministic sum of the lower triangle of the n x n matrix
+__global__ void __launch_bounds__(256) checksum_partial_kernel(const double* __restrict__ A, int64_t n, int64_t ld,
+                                                               double* __restrict__ partial) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x)
+    for (int64_t i = j + threadIdx.x; i < n; i += 256) s += A[j * ld + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void checksum_final_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[b];
+  *out = s;
+}
+
 struct cocons_ctx {
   int device = 0;
   int64_t n = 0, n_pad = 0, p = 0, r = 0, q = 0;
@@ -215,6 +236,8 @@ struct cocons_ctx {
   double* dTap = nullptr;
   int64_t tap_nnz = 0;
   bool factor_is_taper = false;
+  double* dCheck = nullptr;  // COCONS_DEBUG_CHECKSUM: 296 partials + [assembly, factor] sums
+  double check[2] = {0, 0};
   SiteTable table() const { return SiteTable{dSite, n_pad, dOrig}; }
   TaperTable taper_table() const { return TaperTable{dSite, n_pad}; }  // shares the per-site buffer
 };
@@ -239,6 +262,23 @@ static int check_device(int device) {
   COCONS_CUDA_TRY(cudaSetDevice(device));
   return 0;
 }
+
+// One evaluation at a time per device and process.  Several contexts driven by host threads used to overlap
+// their kernel chains on one GPU (DenseLikelihoodPool); tools/pool_stress.py showed that with two or more
+// factorisations in flight 10-30 % of the results differ from the single-context value by up to 3e-5 relative
+// (assembly checksums identical, factor checksums not; a host synchronisation before every GEMM launch makes
+// the difference vanish, device fences do not).  Until that interaction is understood the kernel chains of
+// different contexts are serialised here - a single context is bit-reproducible and is what the parity tests
+// cover.  COCONS_CONCURRENT_EVALS=1 removes the lock (for investigating, not for results).
+static std::mutex g_device_mutex[16];
+struct DeviceGuard {
+  std::unique_lock<std::mutex> lk;
+  explicit DeviceGuard(int device) {
+    static int concurrent = -1;
+    if (concurrent < 0) concurrent = getenv("COCONS_CONCURRENT_EVALS") ? 1 : 0;
+    if (!concurrent && device >= 0 && device < 16) lk = std::unique_lock<std::mutex>(g_device_mutex[device]);
+  }
+};
 
 // device of the stateless / one-shot entry points: COCONS_DEVICE (one R worker per GPU sets it), default 0
 static int default_device() {
@@ -394,7 +434,7 @@ void cocons_ctx_destroy(cocons_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->dX), cudaFree(c->dLocs), cudaFree(c->dZ), cudaFree(c->dXb), cudaFree(c->dTheta), cudaFree(c->dSite);
   cudaFree(c->dOrig), cudaFree(c->dA), cudaFree(c->dRhs);
-  cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dInv), cudaFree(c->dTap);
+  cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dInv), cudaFree(c->dTap), cudaFree(c->dCheck);
   chol_workspace_destroy(&c->ws);
   cudaFree(c->dGram);
   if (c->hStage) cudaFreeHost(c->hStage);
@@ -519,9 +559,21 @@ static int assemble_and_factor(cocons_ctx* c, int par, const double* theta6, con
     launch_assemble_lower(c->n, np, c->table(), c->global_range, c->nu_fixed, c->mode, c->dA, np, c->stream);
   }
   c->factor_is_taper = taper;
+  static int debug_checksum = -1;
+  if (debug_checksum < 0) debug_checksum = getenv("COCONS_DEBUG_CHECKSUM") ? 1 : 0;
+  if (debug_checksum) {
+    if (!c->dCheck) COCONS_CUDA_TRY(cudaMalloc(&c->dCheck, sizeof(double) * 304));
+    checksum_partial_kernel<<<296, 256, 0, c->stream>>>(c->dA, c->n, np, c->dCheck);
+    checksum_final_kernel<<<1, 1, 0, c->stream>>>(c->dCheck, 296, c->dCheck + 300);
+  }
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
   chol_factor(c->dA, np, np, c->ws, c->stream);
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+  if (debug_checksum) {
+    checksum_partial_kernel<<<296, 256, 0, c->stream>>>(c->dA, c->n, np, c->dCheck);
+    checksum_final_kernel<<<1, 1, 0, c->stream>>>(c->dCheck, 296, c->dCheck + 301);
+    COCONS_CUDA_TRY(cudaMemcpyAsync(c->check, c->dCheck + 300, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
   COCONS_CUDA_TRY(cudaGetLastError());
   c->factor_valid = false;
   return 0;
@@ -562,6 +614,7 @@ static int n2ll_impl(cocons_ctx* c, int kind, const double* theta6, const double
     return COCONS_ERR_ARG;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, kind == COCONS_ML ? mean_p : nullptr, taper);
   if (rc) return rc;
   const int64_t np = c->n_pad, p = c->p;
@@ -791,6 +844,7 @@ int cocons_profile_betas(cocons_ctx* c, int kind, double* betas) {
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad;
   const int qx = (kind == COCONS_PROFILE) ? (int)c->q : (int)c->p;
   if (qx <= 0 || qx >= kMaxRhs) {
@@ -843,6 +897,7 @@ int cocons_factor(cocons_ctx* c, int par, const double* theta6, const double* li
     return COCONS_ERR_ARG;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, par, theta6, limits, nullptr);
   if (rc) return rc;
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -956,6 +1011,7 @@ static int predict_impl(cocons_ctx* c, int64_t m, const double* locs_pred, const
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   int rc = 0;
   if (tp) {
     // cov_rns_taper_pred always takes the smoothness through the logistic, for both site sets (:54-70)
@@ -1029,6 +1085,7 @@ int cocons_factor_taper(cocons_ctx* c, const double* theta6, const double* limit
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, nullptr, true);
   if (rc) return rc;
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -1072,6 +1129,7 @@ int cocons_sim(cocons_ctx* c, int64_t k, const double* eps, double* out) {
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad;
   cudaStream_t st = c->stream;
   double *dE = nullptr, *dO = nullptr;
@@ -1119,6 +1177,7 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad, p = c->p, mp = round_up(m, kTile);
   cudaStream_t st = c->stream;
   // covmat_unobs = cov_rns(theta, locs_pred, X_pred, limits) with the factor's own mode (R/sim.R:99-102)
@@ -1196,6 +1255,12 @@ int cocons_ctx_get_factor(cocons_ctx* c, double* L, int64_t* perm) {
 int cocons_ctx_timings(cocons_ctx* c, double* ms4) {
   if (!c || !ms4) return COCONS_ERR_ARG;
   for (int i = 0; i < 4; ++i) ms4[i] = c->ms[i];
+  return 0;
+}
+
+int cocons_ctx_debug_checksums(cocons_ctx* c, double* out2) {
+  if (!c || !out2) return COCONS_ERR_ARG;
+  out2[0] = c->check[0], out2[1] = c->check[1];
   return 0;
 }
 

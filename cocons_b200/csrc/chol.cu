@@ -325,12 +325,20 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 // mode 0: C -= A B^T on 128 x 64 tiles, 8 warps, two CTAs per SM; mode 1: C = A B^T on 128 x 128 tiles,
 // 16 warps, one CTA per SM - the in-place panel solve needs one CTA to own the whole 128-column block
 // it overwrites (every bulk copy of its A rows has landed before its first store).
+// COCONS_DEBUG_SYNC=1: host-synchronise the stream before every GEMM launch (bisection aid)
+static int debug_sync_mode() {
+  static int m = -1;
+  if (m < 0) m = getenv("COCONS_DEBUG_SYNC") ? 1 : 0;
+  return m;
+}
+
 void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                     int64_t ldb, double* C, int64_t ldc, int lower_only, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return;
   static bool attr_done[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
+  if (debug_sync_mode()) cudaStreamSynchronize(st);
   if (dev < 16 && !attr_done[dev]) {
     cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          GemmCfg<64, 2>::kSmemBytes + 64);
@@ -538,6 +546,268 @@ __global__ void __launch_bounds__(256, 1)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Diagonal tile, blocked variant (K3b).  The register-resident kernel above spends ~1000 clocks on each
+// of its 128 column steps (pivot -> rsqrt -> publish -> mbarrier round trip); this one shortens the
+// sequential part to what is inherently sequential - the 16 pivots of a 16 x 16 diagonal block, done by
+// ONE warp - and moves everything else into 16 x 16 x 16 block products on the FP64 tensor cores
+// (DMMA.8x8x4), spread over the 8 warps.  The tile and the running inverse live in shared memory as
+// 36 + 36 lower blocks of 16 x 16, column-major with a column stride of 20 doubles (every DMMA fragment
+// fetch and the coalesced tile load / store are bank-conflict free).
+//
+// Block step s = 0..7, with T the forward-eliminated identity (T = I at the start):
+//   P1 (warp 0)   L_ss = chol(A_ss),  W_ss = L_ss^-1                (16 sequential pivots)
+//   P2 (8 warps)  L_as = A_as W_ss^T            a > s               W_sc = W_ss T_sc        c < s
+//   P3 (8 warps)  A_ab -= L_as L_bs^T    s < b <= a                 T_ac -= L_as W_sc    a > s, c <= s
+// after which W = L^-1.  Same outputs as potrf_tile_kernel: L over the tile (strict upper part zeroed),
+// W as a 128 x 128 column-major matrix, first failing pivot (1-based, dpotrf's info) in *info.
+// ---------------------------------------------------------------------------
+constexpr int PB = 16;                        // block edge
+constexpr int PNB = PT / PB;                  // 8 block rows
+constexpr int PBS = 20;                       // column stride of a block in shared memory (== 4 mod 16)
+constexpr int PBLK = PB * PBS;                // doubles per block
+constexpr int PNBLK = PNB * (PNB + 1) / 2;    // 36 lower blocks
+constexpr int kPotrfBlockedSmem = 2 * PNBLK * PBLK * (int)sizeof(double) + 16;
+#ifdef COCONS_POTRF_PROBE
+__device__ long long g_probe_b[64];
+#define PROBEB(slot) if (threadIdx.x == 0) g_probe_b[slot] = clock64()
+#else
+#define PROBEB(slot)
+#endif
+
+__device__ __forceinline__ int pblk(int a, int b) { return (a * (a + 1) / 2 + b) * PBLK; }  // a >= b
+
+// Blocks are stored COLUMN-major in shared memory: element (i, j) of a block at [i + j PBS].
+//
+// One warp: C (16 x 16) = X Y (MODE 0) or C -= X Y (MODE 1), X(i,k) at X[i sxi + k sxk], Y(k,j) at
+// Y[k syk + j syj].  Every operand fragment is fetched before the first store, so C may alias X or Y.
+// The product is formed transposed (D' = Y^T X^T) so that the two accumulators of a lane are two
+// consecutive ROWS of one column of C - contiguous in the column-major block.  mma.m8n8k4.f64 fragments:
+// a = A[g][c4], b = B[c4][g], d = D[g][2 c4 + {0,1}]; here A = Y^T (m = column of C), B = X^T (n = row of C).
+// A dependent DMMA chain costs ~200 clocks per link, so the 16 products of a block go to 16 independent
+// accumulator pairs and are summed afterwards.
+template <int MODE>
+__device__ __forceinline__ void bmm16(double* C, const double* X, int sxi, int sxk, const double* Y, int syk, int syj,
+                                      int lane) {
+  const int g = lane >> 2, c4 = lane & 3;
+  double xb[2][4], ya[2][4];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      xb[q][kc] = X[(8 * q + g) * sxi + (4 * kc + c4) * sxk];
+      ya[q][kc] = Y[(4 * kc + c4) * syk + (8 * q + g) * syj];
+    }
+  __syncwarp();
+  double d[2][2][4][2];
+#pragma unroll
+  for (int qi = 0; qi < 2; ++qi)
+#pragma unroll
+    for (int qj = 0; qj < 2; ++qj)
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        d[qi][qj][kc][0] = d[qi][qj][kc][1] = 0.0;
+        // D'[m = g -> column 8 qj + g][n = 2 c4 + {0,1} -> row 8 qi + 2 c4 + {0,1}]
+        dmma884(d[qi][qj][kc][0], d[qi][qj][kc][1], ya[qj][kc], xb[qi][kc]);
+      }
+#pragma unroll
+  for (int qi = 0; qi < 2; ++qi)
+#pragma unroll
+    for (int qj = 0; qj < 2; ++qj) {
+      const double s0 = (d[qi][qj][0][0] + d[qi][qj][1][0]) + (d[qi][qj][2][0] + d[qi][qj][3][0]);
+      const double s1 = (d[qi][qj][0][1] + d[qi][qj][1][1]) + (d[qi][qj][2][1] + d[qi][qj][3][1]);
+      double2* p = reinterpret_cast<double2*>(C + (8 * qj + g) * PBS + 8 * qi + 2 * c4);
+      double2 v;
+      if (MODE) {
+        v = *p;
+        v.x -= s0;
+        v.y -= s1;
+      } else {
+        v.x = s0;
+        v.y = s1;
+      }
+      *p = v;
+    }
+}
+
+// P1 of block step s, one warp: L_ss = chol(A_ss) in place, then W_ss = L_ss^-1 in place of the identity
+// block.  Lane j < 16 owns COLUMN j in registers.  Pivot step k: lane k takes the reciprocal square root
+// of its diagonal entry, scales its column and stores it - that IS column k of L_ss in the block - then
+// every lane j > k pulls l_jk and the broadcast l_ik from there: one __syncwarp per pivot, no shuffles.
+// The inverse follows by forward substitution on the columns of the identity (an FMA chain of depth 16).
+__device__ __forceinline__ void potrf_diag_block(double* Dl, double* Dt, double* rinvs, int lane, int* fail,
+                                                 int* info, int first_pivot) {
+  const int j = lane & 15;
+  const bool active = lane < 16;
+  double v[PB];
+#pragma unroll
+  for (int i = 0; i < PB; i += 2) {
+    const double2 x = *reinterpret_cast<const double2*>(Dl + j * PBS + i);
+    v[i] = x.x;
+    v[i + 1] = x.y;
+  }
+#pragma unroll
+  for (int k = 0; k < PB; ++k) {
+    if (active && j == k) {
+      const double d = v[k];
+      if (!(d > 0.0) && atomicCAS(fail, 0, 1) == 0) atomicCAS(info, 0, first_pivot + k + 1);  // dpotrf's info
+      const double rinv = rsqrt(d);  // (a float-seeded Newton variant measured slower: 305 vs ~160 clocks)
+      rinvs[k] = rinv;
+      v[k] = d * rinv;
+#pragma unroll
+      for (int i = k + 1; i < PB; ++i) v[i] *= rinv;
+#pragma unroll
+      for (int i = 0; i < PB; i += 2) {  // column k of L_ss (rows above k are never read)
+        double2 x;
+        x.x = v[i];
+        x.y = v[i + 1];
+        *reinterpret_cast<double2*>(Dl + k * PBS + i) = x;
+      }
+    }
+    __syncwarp();
+    if (active && j > k) {
+      const double ljk = Dl[k * PBS + j];
+#pragma unroll
+      for (int i = k + 1; i < PB; ++i)
+        if (i >= j) v[i] = fma(-Dl[k * PBS + i], ljk, v[i]);
+    }
+  }
+  // W_ss: lane c owns column c of the eliminated identity; t[k] is final when step k starts
+  if (active) {
+    double t[PB];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) t[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < PB - 1; ++k) {
+      const double tk = t[k] * rinvs[k];  // zero while k < column
+#pragma unroll
+      for (int i = k + 1; i < PB; ++i) t[i] = fma(-Dl[k * PBS + i], tk, t[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < PB; i += 2) {
+      double2 x;
+      x.x = t[i] * rinvs[i];
+      x.y = t[i + 1] * rinvs[i + 1];
+      *reinterpret_cast<double2*>(Dt + j * PBS + i) = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+    potrf_tile_blocked_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int* __restrict__ info,
+                              int first_index) {
+  extern __shared__ __align__(16) double psm[];
+  double* Lb = psm;                  // lower blocks of the tile -> L
+  double* Tb = psm + PNBLK * PBLK;   // lower blocks of T -> W
+  __shared__ int fail;
+  __shared__ double rinvs[PB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) fail = 0;
+  PROBEB(0);
+  // load: column-major sweep of the tile (coalesced 16-byte loads), lower blocks only; T = 0 off the
+  // diagonal blocks (the diagonal blocks of T are written by P1)
+#pragma unroll 8
+  for (int idx = tid; idx < PT * PT / 2; idx += 256) {
+    const int i = (2 * idx) & (PT - 1), j = (2 * idx) >> 7;
+    const int a = i >> 4, b = j >> 4;
+    if (a >= b) {
+      const double2 x = *reinterpret_cast<const double2*>(A + (int64_t)j * ld + i);
+      const int off = pblk(a, b) + (j & 15) * PBS + (i & 15);
+      *reinterpret_cast<double2*>(Lb + off) = x;
+      *reinterpret_cast<double2*>(Tb + off) = make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  PROBEB(1);
+
+  // s = -1 is the prologue (P1 of block 0 only); the diagonal-block routine has ONE call site so that its
+  // fully unrolled code is fetched into the instruction cache once
+  for (int s = -1; s < PNB; ++s) {
+    if (s >= 0) {
+      PROBEB(2 + 3 * s);
+      if (fail) return;
+      double* Dt = Tb + pblk(s, s);  // W_ss
+      // ---- P2: panel blocks L_as = A_as W_ss^T (a > s) and the new block row of W, W_sc = W_ss T_sc (c < s)
+      int t = 0;
+      for (int a = s + 1; a < PNB; ++a, ++t)
+        if ((t & 7) == warp) bmm16<0>(Lb + pblk(a, s), Lb + pblk(a, s), 1, PBS, Dt, PBS, 1, lane);
+      for (int c = 0; c < s; ++c, ++t)
+        if ((t & 7) == warp) bmm16<0>(Tb + pblk(s, c), Dt, 1, PBS, Tb + pblk(s, c), 1, PBS, lane);
+      __syncthreads();
+      PROBEB(3 + 3 * s);
+    }
+    // ---- P3: trailing update A_ab -= L_as L_bs^T (s < b <= a) and T_ac -= L_as W_sc (a > s, c <= s).
+    // Look-ahead: warp 0 updates only the next diagonal block and factors it (P1 of step s + 1) while the
+    // other seven warps do the rest.
+    if (warp == 0) {
+      if (s + 1 < PNB) {
+        if (s >= 0) {
+          bmm16<1>(Lb + pblk(s + 1, s + 1), Lb + pblk(s + 1, s), 1, PBS, Lb + pblk(s + 1, s), PBS, 1, lane);
+          __syncwarp();
+        }
+        potrf_diag_block(Lb + pblk(s + 1, s + 1), Tb + pblk(s + 1, s + 1), rinvs, lane, &fail, info,
+                         first_index + (s + 1) * PB);
+      }
+    } else if (s >= 0) {
+      int t = 0;
+      for (int a = s + 1; a < PNB; ++a) {
+        for (int b = s + 1; b <= a; ++b) {
+          if (a == s + 1 && b == s + 1) continue;  // warp 0's block
+          if (t++ % 7 == warp - 1)
+            bmm16<1>(Lb + pblk(a, b), Lb + pblk(a, s), 1, PBS, Lb + pblk(b, s), PBS, 1, lane);
+        }
+        for (int c = 0; c <= s; ++c)
+          if (t++ % 7 == warp - 1)
+            bmm16<1>(Tb + pblk(a, c), Lb + pblk(a, s), 1, PBS, Tb + pblk(s, c), 1, PBS, lane);
+      }
+    }
+    __syncthreads();
+    if (s >= 0) PROBEB(4 + 3 * s);
+  }
+
+  // store: L over the tile (strict upper part zeroed), W = L^-1 column-major, zero above the diagonal
+#pragma unroll 4
+  for (int idx = tid; idx < PT * PT / 2; idx += 256) {
+    const int i = (2 * idx) & (PT - 1), j = (2 * idx) >> 7;
+    const int a = i >> 4, b = j >> 4;
+    double2 l, w;
+    l.x = l.y = w.x = w.y = 0.0;
+    if (a >= b) {
+      const int off = pblk(a, b) + (j & 15) * PBS + (i & 15);
+      const double2 lv = *reinterpret_cast<const double2*>(Lb + off);
+      const double2 wv = *reinterpret_cast<const double2*>(Tb + off);
+      if (i >= j) l.x = lv.x, w.x = wv.x;
+      if (i + 1 >= j) l.y = lv.y, w.y = wv.y;
+    }
+    *reinterpret_cast<double2*>(A + (int64_t)j * ld + i) = l;
+    *reinterpret_cast<double2*>(Winv + j * PT + i) = w;
+  }
+  PROBEB(30);
+}
+
+// the blocked kernel is the default (53.8 vs 81.0 us per cold tile in tools/micro/potrf_check.cu);
+// COCONS_POTRF=1 selects the register-resident column-sweep kernel
+void launch_potrf_tile(double* A, int64_t ld, double* Winv, int* info, int first_index, cudaStream_t st) {
+  static int variant = -1;
+  static bool attr_done[16] = {};
+  if (variant < 0) {
+    const char* e = getenv("COCONS_POTRF");
+    variant = e ? atoi(e) : 2;
+  }
+  note_launch();
+  if (variant == 1) {
+    potrf_tile_kernel<<<1, 256, 0, st>>>(A, ld, Winv, info, first_index);
+    return;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaFuncSetAttribute(potrf_tile_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfBlockedSmem);
+    attr_done[dev] = true;
+  }
+  potrf_tile_blocked_kernel<<<1, 256, kPotrfBlockedSmem, st>>>(A, ld, Winv, info, first_index);
+}
+
 int chol_workspace_create(int64_t n_pad, CholWorkspace* ws) {
   ws->winv = nullptr, ws->info = nullptr, ws->panel_stream = nullptr, ws->ev_a = nullptr, ws->ev_p = nullptr;
   ws->ev_k0 = nullptr, ws->ev_k1 = nullptr;
@@ -572,8 +842,7 @@ void factor_panel(double* A, int64_t n_pad, int64_t ld, const CholWorkspace& ws,
   for (int64_t jj = J0; jj < J0 + jb; ++jj) {
     double* Ajj = A + jj * kTile * ld + jj * kTile;
     double* Wjj = ws.winv + jj * (int64_t)kTile * kTile;
-    note_launch();
-    potrf_tile_kernel<<<1, 256, 0, st>>>(Ajj, ld, Wjj, ws.info, (int)(jj * kTile));
+    launch_potrf_tile(Ajj, ld, Wjj, ws.info, (int)(jj * kTile), st);
     const int64_t below = n_pad - (jj + 1) * kTile;
     if (below <= 0) continue;
     double* panel = Ajj + kTile;  // rows below the diagonal tile, 128 columns
@@ -605,6 +874,12 @@ int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStre
   cudaMemsetAsync(ws.info, 0, sizeof(int), st);
   const int64_t nt = n_pad / kTile;
   const int64_t outer = chol_outer(n_pad);
+  static int lookahead = -1;  // COCONS_CHOL_LOOKAHEAD=0: panel work on the main stream too (debugging knob)
+  if (lookahead < 0) {
+    const char* e = getenv("COCONS_CHOL_LOOKAHEAD");
+    lookahead = e ? atoi(e) : 1;
+  }
+  cudaStream_t ps = lookahead ? ws.panel_stream : st;
   factor_panel(A, n_pad, ld, ws, 0, std::min<int64_t>(outer, nt), st);
   for (int64_t J0 = 0; J0 < nt; J0 += outer) {
     const int64_t jb = std::min<int64_t>(outer, nt - J0);
@@ -616,9 +891,9 @@ int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStre
     const double* P = A + J0 * kTile * ld + done;  // rows [done, n_pad) of panel J
     launch_gemm_nt(0, trail, wnext, jb * kTile, P, ld, P, ld, A + done * ld + done, ld, 1, st);  // (a)
     cudaEventRecord(ws.ev_a, st);
-    cudaStreamWaitEvent(ws.panel_stream, ws.ev_a, 0);
-    factor_panel(A, n_pad, ld, ws, J0 + jb, nb_next, ws.panel_stream);
-    cudaEventRecord(ws.ev_p, ws.panel_stream);
+    cudaStreamWaitEvent(ps, ws.ev_a, 0);
+    factor_panel(A, n_pad, ld, ws, J0 + jb, nb_next, ps);
+    cudaEventRecord(ws.ev_p, ps);
     const int64_t rest = trail - wnext;
     if (rest > 0) {  // (b)
       const double* P2 = P + wnext;

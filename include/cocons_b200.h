@@ -193,6 +193,11 @@ int cocons_ctx_get_factor(cocons_ctx* ctx, double* L, int64_t* perm);
  * the context's stream): [0] site+assembly [1] factorisation [2] solves+reductions [3] total */
 int cocons_ctx_timings(cocons_ctx* ctx, double* ms4);
 
+/* debugging aid: with COCONS_DEBUG_CHECKSUM=1 in the environment every evaluation also forms the
+ * (deterministic) sum of the lower triangle after the assembly [0] and after the factorisation [1];
+ * used by tools/pool_stress.py to localise differences between concurrent evaluations */
+int cocons_ctx_debug_checksums(cocons_ctx* ctx, double* out2);
+
 /* duration (ms, CUDA events inside the evaluation) and flop count of the LARGEST trailing-update launch of
  * the last factorisation - the dominant kernel's own roofline point (bench.py) */
 int cocons_ctx_kernel_timing(cocons_ctx* ctx, double* ms, double* flops);

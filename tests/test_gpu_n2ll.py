@@ -155,3 +155,31 @@ def test_dmma_trailing_update_kernel_runs_at_speed():
     tflops = flops / (ms.value * 1e-3) / 1e12
     print("SYRK n=%d k=%d: %.3f ms, %.1f TFLOP/s" % (n, k, ms.value, tflops))
     assert tflops > 5.0
+
+
+def test_pooled_evaluations_are_bit_identical_to_single_context(datasets):
+    """Several evaluations submitted from host threads (DenseLikelihoodPool, the batched finite-difference
+    gradient of cocoOptim / getHessian) must give exactly the values a single context gives: the library
+    serialises the kernel chains of different contexts per device (tools/pool_stress.py found that
+    overlapping factorisations are not reproducible)."""
+    H = datasets["holes_training"]
+    n = 3000
+    X = cb.getScale(np.column_stack([np.ones(n), H[:n, 2], H[:n, 3]]))["std.covs"]
+    base = {"mean": np.zeros(3), "std.dev": np.array([0.2, 0.15, 0.1]), "scale": np.array([-1.6, 0.2, -0.15]),
+            "aniso": np.array([0.1, 0.2, -0.1]), "tilt": np.array([0.3, -0.2, 0.1]),
+            "smooth": np.array([0.2, 0.3, -0.2]), "nugget": np.array([-4, 0.1, 0.1])}
+    pts = []
+    for k in range(16):
+        t = {a: v.copy() for a, v in base.items()}
+        t["scale"][0] += 1e-4 * k
+        pts.append(t)
+
+    def f(ctx, t):
+        r = ctx.terms(_lib.ML, t, [0.5, 2.5], t["mean"])
+        return r["logdet"], float(r["quad"][0])
+
+    with cb.DenseLikelihood(H[:n, :2], X, H[:n, 4]) as ctx:
+        ref = [f(ctx, t) for t in pts]
+    with cb.DenseLikelihoodPool(H[:n, :2], X, H[:n, 4], size=4) as pool:
+        for _ in range(2):
+            assert pool.map(f, pts) == ref
