@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
         hi.x = acc[a][2 * u][1];
         hi.y = acc[a][2 * u + 1][1];
       } else {
-        lo = __ldcg(p);  // C was written by an earlier kernel, possibly through another SM: read it from L2
-        hi = __ldcg(p + 1);
+        lo = __ldcv(p);  // C was written by an earlier kernel, possibly through another SM: never from a stale L1 line
+        hi = __ldcv(p + 1);
         lo.x -= acc[a][2 * u][0];
         lo.y -= acc[a][2 * u + 1][0];
         hi.x -= acc[a][2 * u][1];
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       w[a][b] = 0.0;
-      r[a][b] = (a >= b) ? __ldcg(A + (int64_t)(tx + 16 * b) * ld + ty + 16 * a) : 0.0;
+      r[a][b] = (a >= b) ? __ldcv(A + (int64_t)(tx + 16 * b) * ld + ty + 16 * a) : 0.0;
     }
   if (tid == 0) {
     fail = 0;
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(256, 1)
     const int i = (2 * idx) & (PT - 1), j = (2 * idx) >> 7;
     const int a = i >> 4, b = j >> 4;
     if (a >= b) {
-      const double2 x = __ldcg(reinterpret_cast<const double2*>(A + (int64_t)j * ld + i));
+      const double2 x = __ldcv(reinterpret_cast<const double2*>(A + (int64_t)j * ld + i));
       const int off = pblk(a, b) + (j & 15) * PBS + (i & 15);
       *reinterpret_cast<double2*>(Lb + off) = x;
       *reinterpret_cast<double2*>(Tb + off) = make_double2(0.0, 0.0);
