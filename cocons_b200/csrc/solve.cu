@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(256) fwd_solve_coop_kernel(const double* __res
       if (tid < kTile) {
 #pragma unroll
         for (int c = 0; c < NR; ++c)
-          if (c < nr) B[(int64_t)c * ldb + i0 + tid] -= part[c][tid] + part[c][tid + kTile];
+          if (c < nr) {  // this row block was last updated by ANOTHER CTA (previous step): read it from L2
+            double* bp = B + (int64_t)c * ldb + i0 + tid;
+            *bp = __ldcg(bp) - (part[c][tid] + part[c][tid + kTile]);
+          }
       }
       __syncthreads();
     }
