@@ -114,6 +114,104 @@ __global__ void __launch_bounds__(256) fwd_solve_coop_kernel(const double* __res
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same substitution WITHOUT a cooperative launch: two ordinary kernels per tile step (y_J = W_J b_J by one
+// CTA; b_I -= L_IJ y_J by one CTA per remaining tile row), same arithmetic and summation order as the
+// cooperative kernel.  Opt-in (COCONS_SOLVE_COOP=0): written at the end of round 1 to test whether the
+// cooperative launch is what makes overlapping evaluations irreproducible; it costs 2 n/128
+// launches per solve instead of one and has not been run on a GPU yet.
+// ---------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256) fwd_tile_solve_kernel(const double* __restrict__ W, double* __restrict__ B,
+                                                             double* __restrict__ Y, int64_t ldb, int64_t j0, int nr) {
+  __shared__ double bj[NR][kTile];
+  __shared__ double part[NR][256];
+  const int tid = threadIdx.x;
+  const int row = tid & (kTile - 1), h = tid >> 7;
+  for (int idx = tid; idx < NR * kTile; idx += 256) {
+    const int c = idx / kTile, k = idx % kTile;
+    bj[c][k] = (c < nr) ? __ldcg(B + (int64_t)c * ldb + j0 + k) : 0.0;
+  }
+  __syncthreads();
+  double acc[NR];
+#pragma unroll
+  for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+  const double* Wp = W + (int64_t)h * (kTile / 2) * kTile + row;
+#pragma unroll 16
+  for (int k = 0; k < kTile / 2; ++k) {
+    const double w = __ldg(Wp + (int64_t)k * kTile);
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = fma(w, bj[c][h * (kTile / 2) + k], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
+  __syncthreads();
+  if (tid < kTile) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c)
+      if (c < nr) Y[(int64_t)c * ldb + j0 + tid] = part[c][tid] + part[c][tid + kTile];
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256) fwd_tile_update_kernel(const double* __restrict__ L, int64_t ld,
+                                                              const double* __restrict__ Y, double* __restrict__ B,
+                                                              int64_t ldb, int64_t J, int nr) {
+  __shared__ double yj[NR][kTile];
+  __shared__ double part[NR][256];
+  const int tid = threadIdx.x;
+  const int row = tid & (kTile - 1), h = tid >> 7;
+  const int64_t j0 = J * kTile, i0 = (J + 1 + blockIdx.x) * kTile;
+  for (int idx = tid; idx < NR * kTile; idx += 256) {
+    const int c = idx / kTile, k = idx % kTile;
+    yj[c][k] = (c < nr) ? __ldcg(Y + (int64_t)c * ldb + j0 + k) : 0.0;
+  }
+  __syncthreads();
+  double acc[NR];
+#pragma unroll
+  for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+  const double* Lp = L + (j0 + (int64_t)h * (kTile / 2)) * ld + i0 + row;
+#pragma unroll 16
+  for (int k = 0; k < kTile / 2; ++k) {
+    const double l = __ldg(Lp + (int64_t)k * ld);
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = fma(l, yj[c][h * (kTile / 2) + k], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NR; ++c) part[c][tid] = acc[c];
+  __syncthreads();
+  if (tid < kTile) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c)
+      if (c < nr) {
+        double* bp = B + (int64_t)c * ldb + i0 + tid;
+        *bp = __ldcg(bp) - (part[c][tid] + part[c][tid + kTile]);
+      }
+  }
+}
+
+template <int NR>
+static void launch_fwd_steps(const double* L, int64_t ld, const double* winv, double* B, double* Y, int64_t ldb,
+                             int64_t nt, int nr, cudaStream_t st) {
+  for (int64_t J = 0; J < nt; ++J) {
+    note_launch();
+    fwd_tile_solve_kernel<NR><<<1, 256, 0, st>>>(winv + J * (int64_t)kTile * kTile, B, Y, ldb, J * kTile, nr);
+    if (J + 1 < nt) {
+      note_launch();
+      fwd_tile_update_kernel<NR><<<(unsigned)(nt - J - 1), 256, 0, st>>>(L, ld, Y, B, ldb, J, nr);
+    }
+  }
+}
+
+static bool solve_uses_cooperative_launch() {
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("COCONS_SOLVE_COOP");
+    coop = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return coop != 0;
+}
+
 template <int NR>
 static void launch_fwd_coop(const double* L, int64_t ld, const double* winv, double* B, double* Y, int64_t ldb,
                             int64_t nt, int nr, cudaStream_t st) {
@@ -125,6 +223,10 @@ static void launch_fwd_coop(const double* L, int64_t ld, const double* winv, dou
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_solve_coop_kernel<NR>, 256, 0);
     max_blocks[dev] = sms * (per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm));
+  }
+  if (!solve_uses_cooperative_launch()) {
+    launch_fwd_steps<NR>(L, ld, winv, B, Y, ldb, nt, nr, st);
+    return;
   }
   int grid = (dev < 16) ? max_blocks[dev] : 148;
   if (grid > nt) grid = (int)(nt > 0 ? nt : 1);
