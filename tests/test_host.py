@@ -160,3 +160,51 @@ def test_r_glue_compiles_and_registers_the_reference_entry_points():
                "GetNeg2loglikelihood <- function(theta, par.pos, locs, x_covariates, smooth.limits, z, n, lambda, "
                "safe = TRUE)"):
         assert fn in rsrc
+
+
+def test_spam_stand_ins_against_brute_force():
+    """nearest_dist (kd-tree) against an O(n m) distance threshold, on random sites incl. duplicates; the
+    spam slot holder round-trips through a dense array."""
+    rng = np.random.default_rng(12)
+    for n, m, delta in ((1, 1, 0.5), (40, 0, 0.3), (75, 31, 0.45), (64, 64, 0.0)):
+        x = rng.uniform(-1, 1, (n, 2))
+        if n > 3:
+            x[3] = x[1]
+        y = None if m == 0 else rng.uniform(-1, 1, (m, 2))
+        if m > 5:
+            y[5] = x[0]
+        sp = cb.nearest_dist(x, y, delta=delta)
+        yy = x if y is None else y
+        d = np.sqrt((x[:, None, 0] - yy[None, :, 0]) ** 2 + (x[:, None, 1] - yy[None, :, 1]) ** 2)
+        keep = d <= delta
+        assert sp.dimension == (n, yy.shape[0])
+        assert sp.rowpointers[0] == 1 and sp.rowpointers[-1] - 1 == keep.sum() == sp.entries.shape[0]
+        rows = np.repeat(np.arange(n), np.diff(sp.rowpointers))
+        assert np.array_equal(np.argwhere(keep), np.column_stack([rows, sp.colindices - 1]))  # row-major, ascending
+        assert np.allclose(sp.entries, d[keep], rtol=0, atol=1e-15)
+        dense = cb.cov_wend1(sp, (max(delta, 1e-9), 1)).toarray()
+        assert dense.shape == (n, yy.shape[0]) and np.all(dense[~keep] == 0)
+        if y is None and delta > 0:
+            assert np.all(np.diag(dense) == 1.0) and np.allclose(dense, dense.T)
+    assert sp.colindices.dtype == np.int32 and sp.rowpointers.dtype == np.int32
+
+
+def test_taper_entry_points_validate_the_pattern_before_touching_a_device():
+    th = {k: np.zeros(2) for k in _lib.ASPECTS}
+    locs, X = np.zeros((3, 2)), np.ones((3, 2))
+    with pytest.raises(cb.CoconsError, match="malformed pattern"):
+        cb.cov_rns_taper(th, locs, X, [1, 2, 3], [1, 2, 3, 5], [0.5, 2.5])  # rowpointers end beyond nnz + 1
+    with pytest.raises(cb.CoconsError, match="malformed pattern"):
+        cb.cov_rns_taper(th, locs, X, [1, 2, 3], [0, 1, 2, 3], [0.5, 2.5])  # 0-based rowpointers
+    with pytest.raises(cb.CoconsError, match="outside"):
+        cb.cov_rns_taper(th, locs, X, [1, 2, 4], [1, 2, 3, 4], [0.5, 2.5])  # column 4 of 3
+    with pytest.raises(cb.CoconsError, match="decrease"):
+        cb.cov_rns_taper(th, locs, X, [1, 2, 3], [1, 3, 2, 4], [0.5, 2.5])
+    with pytest.raises(ValueError, match="only for sparse"):
+        cb.getDensityFromDelta(cb.coco("dense", {"a": np.zeros(3)}, locs, np.zeros(3),
+                                       {"std.dev": "~ 1", "scale": "~ 1"}), 0.1)
+    with pytest.raises(ValueError, match="taper"):
+        cb.coco("sparse", {"a": np.zeros(3)}, locs, np.zeros(3), {"std.dev": "~ 1", "scale": "~ 1"})
+    with pytest.raises(ValueError, match="dense"):
+        cb.coco("dense", {"a": np.zeros(3)}, locs, np.zeros(3), {"std.dev": "~ 1", "scale": "~ 1"},
+                info={"taper": cb.cov_wend1, "delta": 0.1})
