@@ -813,6 +813,8 @@ int chol_workspace_create(int64_t n_pad, CholWorkspace* ws) {
   ws->ev_k0 = nullptr, ws->ev_k1 = nullptr;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority (numerically lowest)
+  if (const char* e = getenv("COCONS_PANEL_PRIORITY"))  // 0: panel stream at default priority (bisection aid)
+    if (atoi(e) == 0) hi = 0;
   if (cudaMalloc(&ws->winv, sizeof(double) * (n_pad / kTile) * kTile * kTile) != cudaSuccess ||
       cudaMalloc(&ws->info, sizeof(int)) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ws->panel_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
