@@ -30,7 +30,13 @@ namespace cocons {
 // consecutive rows (32 B) and a quad 128 contiguous bytes of a column.  The
 // same binding makes every operand fetch one conflict-free LDS.128.
 // ---------------------------------------------------------------------------
-constexpr int GBM = 128, GBK = 16, GSTAGES = 4;
+#ifndef COCONS_GEMM_RELEASE
+#define COCONS_GEMM_RELEASE 1
+#endif
+#ifndef COCONS_GEMM_STAGES
+#define COCONS_GEMM_STAGES 4
+#endif
+constexpr int GBM = 128, GBK = 16, GSTAGES = COCONS_GEMM_STAGES;
 constexpr int GLDA = GBM + 4;  // padded leading dimension of a shared k-row (== 4 mod 16: conflict-free LDS.128)
 
 template <int BN, int NU = 2>
@@ -181,6 +187,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive whose barrier address depends on x and y (zero is 0 at run time, unknown at compile time): the
+// instruction cannot issue before the instructions that produce x and y have completed
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, double x, double y, uint32_t zero) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 xl, xh, yl, yh;\n"
+      "mov.b64 {xl, xh}, %1;\n"
+      "mov.b64 {yl, yh}, %2;\n"
+      "or.b32 xl, xl, yl;\n"
+      "and.b32 xl, xl, %3;\n"
+      "add.u32 xl, xl, %0;\n"
+      "mbarrier.arrive.shared::cta.b64 _, [xl];\n"
+      "}" ::"r"(bar),
+      "d"(x), "d"(y), "r"(zero)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -195,9 +217,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+#ifdef COCONS_GEMM_DST_CTA
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+#endif
 }
 
 template <int BN, int NU, int ASSIGN>
@@ -230,10 +258,15 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 
   const int64_t nkb = K / GBK;
   const uint32_t stage0 = smem_u32(smem);
+  const uint32_t rt_zero = (uint32_t)((uint64_t)lda >> 48);  // 0 for any real leading dimension; not foldable
+  (void)rt_zero;
   auto produce = [&](int64_t ld) {  // one lane
     const int slot = (int)(ld % GSTAGES);
     const int64_t fill = ld / GSTAGES;
     if (fill >= 1) mbar_wait(empty0 + 8 * slot, (uint32_t)((fill - 1) & 1));
+#ifdef COCONS_GEMM_PROXY_FENCE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     const uint32_t fb = full0 + 8 * slot;
     mbar_expect_tx(fb, kStageBytes);
     const uint32_t da = stage0 + (uint32_t)slot * Cfg::kStageDoubles * 8u;
@@ -252,21 +285,43 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 #pragma unroll
     for (int b = 0; b < 2 * NU; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
+#ifndef COCONS_GEMM_NO_PREFETCH
   if (!ASSIGN) {  // pull the C tile towards L2 while the main loop runs
     const double* Cp = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
     for (int l = tid; l < BN * 8; l += Cfg::kThreads)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + (int64_t)(l >> 3) * ldc + (l & 7) * 16));
   }
+#endif
+#if defined(COCONS_GEMM_PLAIN)
+  // bisection variant: no bulk copy, no mbarrier - every k-block is loaded with ordinary (L1-bypassing)
+  // loads into slot 0 between two block barriers
+  for (int64_t it = 0; it < nkb; ++it) {
+    __syncthreads();
+    for (int l = tid; l < GBK * GBM; l += Cfg::kThreads)
+      smem[(l / GBM) * GLDA + (l % GBM)] = __ldcv(Ag + (it * GBK + l / GBM) * lda + (l % GBM));
+    for (int l = tid; l < GBK * BN; l += Cfg::kThreads)
+      smem[GBK * GLDA + (l / BN) * Cfg::kLdb + (l % BN)] = __ldcv(Bg + (it * GBK + l / BN) * ldb + (l % BN));
+    __syncthreads();
+    const int slot = 0;
+#else
   if (warp == 0 && lane == 0)
     for (int s = 0; s < GSTAGES - 1 && s < nkb; ++s) produce(s);
   __syncwarp();
 
   for (int64_t it = 0; it < nkb; ++it) {
     const int64_t ld = it + GSTAGES - 1;
+#ifdef COCONS_GEMM_FIXED_PRODUCER
+    if (ld < nkb && warp == 0 && lane == 0) produce(ld);
+#else
     if (ld < nkb && warp == (int)(it % kWarps) && lane == 0) produce(ld);
+#endif
     __syncwarp();
     const int slot = (int)(it % GSTAGES);
     mbar_wait(full0 + 8 * slot, (uint32_t)((it / GSTAGES) & 1));
+#ifdef COCONS_GEMM_FULL_SYNC
+    __syncthreads();
+#endif
+#endif
     const double* as = smem + (size_t)slot * Cfg::kStageDoubles + iw + 2 * g;
     const double* bs = smem + (size_t)slot * Cfg::kStageDoubles + GBK * GLDA + jw + 2 * g;
 #pragma unroll
@@ -290,9 +345,35 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 #pragma unroll
         for (int b = 0; b < 2 * NU; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
     }
-    __syncwarp();
+#if defined(COCONS_GEMM_PLAIN)
+#elif defined(COCONS_GEMM_SYNC_EMPTY)
+    __syncthreads();  // bisection variant: the slot is handed back by a block barrier AND the empty mbarrier
     if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+#else
+    // Handing the slot back.  The next fill is written by the bulk-copy engine (async proxy) while this
+    // warp read the slot with ordinary LDS (generic proxy): a write-after-read across proxies.  ptxas
+    // places SYNCS.ARRIVE right behind the ISSUE of the last LDS - ahead of the DMMAs that consume the
+    // loaded registers - and the arrive does not wait for the load unit: with the LSU queue backed up
+    // (the co-resident CTA's epilogue), the producer saw the slot free, refilled it, and a late LDS read
+    // a 128-byte piece of the NEXT k-block (round 1's irreproducible factors, profiles/r02_chol_race.md).
+    //   COCONS_GEMM_RELEASE bit 0: fence.proxy.async.shared::cta before the arrive (the documented
+    //     generic->async ordering, same place as CUTLASS's fence_view_async_shared() before consumer_release)
+    //   bit 1: the arrive's address is made data-dependent on two accumulators that between them consume
+    //     every LDS of the stage, so it cannot issue before those loads have delivered
+    __syncwarp();
+#if (COCONS_GEMM_RELEASE & 1)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+#if (COCONS_GEMM_RELEASE & 2)
+    if (lane == 0) mbar_arrive_after(empty0 + 8 * slot, acc[0][2][0], acc[2][0][0], rt_zero);
+#else
+    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+#endif
+#endif
   }
+#ifdef COCONS_GEMM_EXIT_SYNC
+  __syncthreads();  // bisection variant: nobody leaves (or stores) while a warp still reads the pipeline
+#endif
 
   double* Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
 #pragma unroll
@@ -326,6 +407,11 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 // 16 warps, one CTA per SM - the in-place panel solve needs one CTA to own the whole 128-column block
 // it overwrites (every bulk copy of its A rows has landed before its first store).
 // COCONS_DEBUG_SYNC=1: host-synchronise the stream before every GEMM launch (bisection aid)
+#ifdef COCONS_GEMM_ONE_CTA
+constexpr int kGemmExtraSmem = 20 * 1024;  // bisection variant: 120 KB per CTA, so two update CTAs never share an SM
+#else
+constexpr int kGemmExtraSmem = 0;
+#endif
 static int debug_sync_mode() {
   static int m = -1;
   if (m < 0) m = getenv("COCONS_DEBUG_SYNC") ? 1 : 0;
@@ -341,7 +427,7 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
   if (debug_sync_mode()) cudaStreamSynchronize(st);
   if (dev < 16 && !attr_done[dev]) {
     cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64, 2>::kSmemBytes + 64);
+                         GemmCfg<64, 2>::kSmemBytes + 64 + kGemmExtraSmem);
     cudaFuncSetAttribute(gemm_nt_tma_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          GemmCfg<128, 2>::kSmemBytes + 64);
     attr_done[dev] = true;
@@ -356,7 +442,7 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
   } else {
     const int nj = (int)(N / 64);
     const int64_t tiles = total_tiles<2>(ni, nj, lower_only);
-    gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64, st>>>(
+    gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64 + kGemmExtraSmem, st>>>(
         ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
   }
 }

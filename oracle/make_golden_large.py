@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE ONLY (oracle/): -2 loglik goldens at the sizes the metric lives at.
+
+    python -m oracle.make_golden_large --sites 50000 --points base,w0,t0     # ~10 min per point on 8 cores
+    python -m oracle.make_golden_large --sites 20000 --points base
+
+For bench.py's synthetic model (bench.synthetic / bench.THETA / bench.theta_at) the covariance
+matrix is produced by the REFERENCE's own compiled source (oracle/_ref/libcocons_ref.so =
+/root/reference/src/cocons_full.cpp, cov_rns :40-321) and the objective by LAPACK exactly as
+R/neg2loglikelihood.R:183-222 does it (chol -> dpotrf, sum(log(diag)), forwardsolve -> dtrtrs, crossprod).
+
+The reference's pair loop has no threads and no row-range entry, so the n x n matrix is put together
+from calls of the UNMODIFIED cov_rns on subsets of the sites: for site blocks a <= b, cov_rns on the
+sites of a and b together (in their original relative order, so the roles the pair loop gives the
+lower / higher index - kahan operand order, the coincident-site rule :284-286 - are those of the full
+call) yields block (b, a) of the full matrix; an entry of cov_rns depends on its two sites and theta
+only.  `--check` verifies that claim bit for bit against one direct full call at a smaller n.
+The results are appended to tests/golden/n2ll_large.json with their provenance.
+"""
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import cov  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "n2ll_large.json")
+LIMITS = [0.5, 2.5]
+
+_shared = {}
+
+
+def point_theta(name):
+    """Named evaluation points: 'base' = bench.THETA, 'wK' / 'tK' = bench.theta_at(K, 0) (warm-up / timed
+    steps of the default bench count from 0), 'rR' = bench.theta_at(0, R)."""
+    import bench
+    if name == "base":
+        return {k: v.copy() for k, v in bench.THETA.items()}
+    if name[0] in "wt":
+        return bench.theta_at(int(name[1:]), 0)
+    if name[0] == "r":
+        return bench.theta_at(0, int(name[1:]))
+    raise ValueError(name)
+
+
+def _block_pair(args):
+    a, b = args
+    S, n, blocks, theta, locs, X = (_shared[k] for k in ("S", "n", "blocks", "theta", "locs", "X"))
+    ia, ib = blocks[a], blocks[b]
+    idx = ia if a == b else np.concatenate([ia, ib])  # a < b: already in increasing site order
+    sub = cov.cov_rns(theta, locs[idx], X[idx], LIMITS, kind="reference")
+    M = np.frombuffer(S, dtype=np.float64).reshape((n, n), order="F")
+    if a == b:
+        M[np.ix_(ia, ia)] = sub
+    else:
+        na = len(ia)
+        M[np.ix_(ib, ia)] = sub[na:, :na]  # lower block (rows b, columns a)
+    return len(idx)
+
+
+def assemble(theta, locs, X, block, workers):
+    """Full covariance (lower triangle valid) in a shared buffer, by the reference's cov_rns on block pairs."""
+    n = locs.shape[0]
+    S = mp.RawArray(ctypes.c_double, n * n)
+    blocks = [np.arange(s, min(n, s + block)) for s in range(0, n, block)]
+    _shared.update(S=S, n=n, blocks=blocks, theta=theta, locs=locs, X=X)
+    pairs = [(a, b) for a in range(len(blocks)) for b in range(a, len(blocks))]
+    pairs.sort(key=lambda ab: ab[0] != ab[1], reverse=True)  # the big jobs first
+    with mp.get_context("fork").Pool(workers) as pool:
+        for _ in pool.imap_unordered(_block_pair, pairs, chunksize=1):
+            pass
+    return np.frombuffer(S, dtype=np.float64).reshape((n, n), order="F")
+
+
+def objective(M, z, mean_vec, X):
+    """R/neg2loglikelihood.R:200-222 on the assembled matrix (in place): n log 2pi + 2 sum log diag + |L^-1 r|^2."""
+    from scipy.linalg import lapack
+    n = M.shape[0]
+    c, info = lapack.dpotrf(M, lower=1, overwrite_a=1, clean=0)
+    assert info == 0, "dpotrf info=%d" % info
+    logdet = float(np.sum(np.log(np.diagonal(c))))
+    resid = z - X @ mean_vec
+    y, info = lapack.dtrtrs(c, resid, lower=1, trans=0)
+    assert info == 0
+    quad = float(y @ y)
+    return {"logdet_half": logdet, "quad": quad, "neg2loglik": n * np.log(2 * np.pi) + 2 * logdet + quad}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sites", type=int, default=50000)
+    ap.add_argument("--points", default="base")
+    ap.add_argument("--block", type=int, default=2500)
+    ap.add_argument("--workers", type=int, default=os.cpu_count())
+    ap.add_argument("--check", action="store_true", help="block-pair assembly == one direct cov_rns call (n = 3000)")
+    args = ap.parse_args()
+    import bench
+    if args.check:
+        locs, X, z = bench.synthetic(3000)
+        th = point_theta("base")
+        A = assemble(th, locs, X, 700, args.workers)
+        B = cov.cov_rns(th, locs, X, LIMITS, kind="reference")
+        il = np.tril_indices(3000)
+        same = np.array_equal(A[il], B[il])
+        print("block-pair assembly bit-equal to the direct reference call (lower triangle, n=3000):", same)
+        sys.exit(0 if same else 1)
+    n = args.sites
+    locs, X, z = bench.synthetic(n)
+    out = {}
+    if os.path.exists(GOLD):
+        with open(GOLD) as f:
+            out = json.load(f)
+    out.setdefault("generator", "oracle/make_golden_large.py")
+    out.setdefault("covariance", "oracle/_ref/libcocons_ref.so: /root/reference/src/cocons_full.cpp cov_rns (:40-321) compiled "
+                   "unmodified, called on site-block pairs (bit-equal to one full call, --check)")
+    out.setdefault("algebra", "LAPACK dpotrf / dtrtrs (OpenBLAS via scipy), R/neg2loglikelihood.R:200-222")
+    out.setdefault("data", "bench.synthetic(n): numpy PCG64 seed %d; theta = bench.THETA / bench.theta_at" % bench.SEED)
+    cases = out.setdefault("cases", {})
+    for name in args.points.split(","):
+        th = point_theta(name)
+        t0 = time.time()
+        M = assemble(th, locs, X, args.block, args.workers)
+        t1 = time.time()
+        res = objective(M, z, th["mean"], X)
+        t2 = time.time()
+        del M
+        res.update(n=n, point=name, theta={k: [float(x) for x in v] for k, v in th.items()}, assembly_s=round(t1 - t0, 1),
+                   lapack_s=round(t2 - t1, 1), cores=args.workers)
+        cases["n%d_%s" % (n, name)] = res
+        print(name, json.dumps({k: res[k] for k in ("neg2loglik", "logdet_half", "quad", "assembly_s", "lapack_s")}), flush=True)
+        with open(GOLD, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
