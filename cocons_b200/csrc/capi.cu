@@ -263,22 +263,10 @@ static int check_device(int device) {
   return 0;
 }
 
-// One evaluation at a time per device and process.  Several contexts driven by host threads used to overlap
-// their kernel chains on one GPU (DenseLikelihoodPool); tools/pool_stress.py showed that with two or more
-// factorisations in flight 10-30 % of the results differ from the single-context value by up to 3e-5 relative
-// (assembly checksums identical, factor checksums not; a host synchronisation before every GEMM launch makes
-// the difference vanish, device fences do not).  Until that interaction is understood the kernel chains of
-// different contexts are serialised here - a single context is bit-reproducible and is what the parity tests
-// cover.  COCONS_CONCURRENT_EVALS=1 removes the lock (for investigating, not for results).
-static std::mutex g_device_mutex[16];
-struct DeviceGuard {
-  std::unique_lock<std::mutex> lk;
-  explicit DeviceGuard(int device) {
-    static int concurrent = -1;
-    if (concurrent < 0) concurrent = getenv("COCONS_CONCURRENT_EVALS") ? 1 : 0;
-    if (!concurrent && device >= 0 && device < 16) lk = std::unique_lock<std::mutex>(g_device_mutex[device]);
-  }
-};
+// Evaluations of different contexts may overlap on one device: every context owns its stream, matrix and
+// workspace and nothing is shared between their kernel chains.  (Round 1 serialised them behind a per-device
+// lock because overlapping chains gave irreproducible factors; the cause was the slot release of the GEMM
+// pipeline, csrc/chol.cu, fixed in round 2 - tests/test_gpu_repro.py pins the behaviour.)
 
 // device of the stateless / one-shot entry points: COCONS_DEVICE (one R worker per GPU sets it), default 0
 static int default_device() {
@@ -614,7 +602,6 @@ static int n2ll_impl(cocons_ctx* c, int kind, const double* theta6, const double
     return COCONS_ERR_ARG;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, kind == COCONS_ML ? mean_p : nullptr, taper);
   if (rc) return rc;
   const int64_t np = c->n_pad, p = c->p;
@@ -844,7 +831,6 @@ int cocons_profile_betas(cocons_ctx* c, int kind, double* betas) {
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad;
   const int qx = (kind == COCONS_PROFILE) ? (int)c->q : (int)c->p;
   if (qx <= 0 || qx >= kMaxRhs) {
@@ -897,7 +883,6 @@ int cocons_factor(cocons_ctx* c, int par, const double* theta6, const double* li
     return COCONS_ERR_ARG;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, par, theta6, limits, nullptr);
   if (rc) return rc;
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -1011,7 +996,6 @@ static int predict_impl(cocons_ctx* c, int64_t m, const double* locs_pred, const
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   int rc = 0;
   if (tp) {
     // cov_rns_taper_pred always takes the smoothness through the logistic, for both site sets (:54-70)
@@ -1085,7 +1069,6 @@ int cocons_factor_taper(cocons_ctx* c, const double* theta6, const double* limit
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   int rc = assemble_and_factor(c, COCONS_PAR_DIFF, theta6, limits, nullptr, true);
   if (rc) return rc;
   COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -1129,7 +1112,6 @@ int cocons_sim(cocons_ctx* c, int64_t k, const double* eps, double* out) {
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad;
   cudaStream_t st = c->stream;
   double *dE = nullptr, *dO = nullptr;
@@ -1177,7 +1159,6 @@ int cocons_sim_cond(cocons_ctx* c, int64_t m, const double* locs_pred, const dou
     return COCONS_ERR_STATE;
   }
   cudaSetDevice(c->device);
-  DeviceGuard guard(c->device);
   const int64_t np = c->n_pad, p = c->p, mp = round_up(m, kTile);
   cudaStream_t st = c->stream;
   // covmat_unobs = cov_rns(theta, locs_pred, X_pred, limits) with the factor's own mode (R/sim.R:99-102)
@@ -1299,6 +1280,10 @@ int cocons_neg2loglik_dense(int kind, int64_t n, int64_t p, int64_t r, int64_t q
     morton_order(n, locs, c->perm.data());
     c->hX.assign(X, X + (size_t)n * p);
     c->rank_x = -1;
+    // the inverse permutation and any attached taper pattern follow perm: drop them (a taper has to be attached
+    // again after new locations; cocons_n2ll_taper reports COCONS_ERR_STATE otherwise)
+    cudaFree(c->dInv), cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dTap);
+    c->dInv = c->dTapCol = c->dTapRow = nullptr, c->dTap = nullptr, c->tap_nnz = 0;
     std::vector<int> orig((size_t)c->n_pad);
     for (int64_t s = 0; s < c->n_pad; ++s) orig[(size_t)s] = (s < n) ? (int)c->perm[(size_t)s] : (int)s;
     COCONS_CUDA_TRY(cudaMemcpy(c->dOrig, orig.data(), sizeof(int) * c->n_pad, cudaMemcpyHostToDevice));

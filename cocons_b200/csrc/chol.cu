@@ -33,10 +33,7 @@ namespace cocons {
 #ifndef COCONS_GEMM_RELEASE
 #define COCONS_GEMM_RELEASE 1
 #endif
-#ifndef COCONS_GEMM_STAGES
-#define COCONS_GEMM_STAGES 4
-#endif
-constexpr int GBM = 128, GBK = 16, GSTAGES = COCONS_GEMM_STAGES;
+constexpr int GBM = 128, GBK = 16, GSTAGES = 4;
 constexpr int GLDA = GBM + 4;  // padded leading dimension of a shared k-row (== 4 mod 16: conflict-free LDS.128)
 
 template <int BN, int NU = 2>
@@ -217,15 +214,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-#ifdef COCONS_GEMM_DST_CTA
-  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-#endif
 }
 
 template <int BN, int NU, int ASSIGN>
@@ -264,9 +255,6 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
     const int slot = (int)(ld % GSTAGES);
     const int64_t fill = ld / GSTAGES;
     if (fill >= 1) mbar_wait(empty0 + 8 * slot, (uint32_t)((fill - 1) & 1));
-#ifdef COCONS_GEMM_PROXY_FENCE
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
     const uint32_t fb = full0 + 8 * slot;
     mbar_expect_tx(fb, kStageBytes);
     const uint32_t da = stage0 + (uint32_t)slot * Cfg::kStageDoubles * 8u;
@@ -292,36 +280,16 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
       asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + (int64_t)(l >> 3) * ldc + (l & 7) * 16));
   }
 #endif
-#if defined(COCONS_GEMM_PLAIN)
-  // bisection variant: no bulk copy, no mbarrier - every k-block is loaded with ordinary (L1-bypassing)
-  // loads into slot 0 between two block barriers
-  for (int64_t it = 0; it < nkb; ++it) {
-    __syncthreads();
-    for (int l = tid; l < GBK * GBM; l += Cfg::kThreads)
-      smem[(l / GBM) * GLDA + (l % GBM)] = __ldcv(Ag + (it * GBK + l / GBM) * lda + (l % GBM));
-    for (int l = tid; l < GBK * BN; l += Cfg::kThreads)
-      smem[GBK * GLDA + (l / BN) * Cfg::kLdb + (l % BN)] = __ldcv(Bg + (it * GBK + l / BN) * ldb + (l % BN));
-    __syncthreads();
-    const int slot = 0;
-#else
   if (warp == 0 && lane == 0)
     for (int s = 0; s < GSTAGES - 1 && s < nkb; ++s) produce(s);
   __syncwarp();
 
   for (int64_t it = 0; it < nkb; ++it) {
     const int64_t ld = it + GSTAGES - 1;
-#ifdef COCONS_GEMM_FIXED_PRODUCER
-    if (ld < nkb && warp == 0 && lane == 0) produce(ld);
-#else
     if (ld < nkb && warp == (int)(it % kWarps) && lane == 0) produce(ld);
-#endif
     __syncwarp();
     const int slot = (int)(it % GSTAGES);
     mbar_wait(full0 + 8 * slot, (uint32_t)((it / GSTAGES) & 1));
-#ifdef COCONS_GEMM_FULL_SYNC
-    __syncthreads();
-#endif
-#endif
     const double* as = smem + (size_t)slot * Cfg::kStageDoubles + iw + 2 * g;
     const double* bs = smem + (size_t)slot * Cfg::kStageDoubles + GBK * GLDA + jw + 2 * g;
 #pragma unroll
@@ -345,11 +313,6 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 #pragma unroll
         for (int b = 0; b < 2 * NU; ++b) dmma884(acc[a][b][0], acc[a][b][1], fj[a], fi[b]);
     }
-#if defined(COCONS_GEMM_PLAIN)
-#elif defined(COCONS_GEMM_SYNC_EMPTY)
-    __syncthreads();  // bisection variant: the slot is handed back by a block barrier AND the empty mbarrier
-    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-#else
     // Handing the slot back.  The next fill is written by the bulk-copy engine (async proxy) while this
     // warp read the slot with ordinary LDS (generic proxy): a write-after-read across proxies.  ptxas
     // places SYNCS.ARRIVE right behind the ISSUE of the last LDS - ahead of the DMMAs that consume the
@@ -369,11 +332,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 #else
     if (lane == 0) mbar_arrive(empty0 + 8 * slot);
 #endif
-#endif
   }
-#ifdef COCONS_GEMM_EXIT_SYNC
-  __syncthreads();  // bisection variant: nobody leaves (or stores) while a warp still reads the pipeline
-#endif
 
   double* Cg = C + (int64_t)bj * BN * ldc + (int64_t)bi * GBM;
 #pragma unroll
@@ -407,11 +366,6 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
 // 16 warps, one CTA per SM - the in-place panel solve needs one CTA to own the whole 128-column block
 // it overwrites (every bulk copy of its A rows has landed before its first store).
 // COCONS_DEBUG_SYNC=1: host-synchronise the stream before every GEMM launch (bisection aid)
-#ifdef COCONS_GEMM_ONE_CTA
-constexpr int kGemmExtraSmem = 20 * 1024;  // bisection variant: 120 KB per CTA, so two update CTAs never share an SM
-#else
-constexpr int kGemmExtraSmem = 0;
-#endif
 static int debug_sync_mode() {
   static int m = -1;
   if (m < 0) m = getenv("COCONS_DEBUG_SYNC") ? 1 : 0;
@@ -427,7 +381,7 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
   if (debug_sync_mode()) cudaStreamSynchronize(st);
   if (dev < 16 && !attr_done[dev]) {
     cudaFuncSetAttribute(gemm_nt_tma_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64, 2>::kSmemBytes + 64 + kGemmExtraSmem);
+                         GemmCfg<64, 2>::kSmemBytes + 64);
     cudaFuncSetAttribute(gemm_nt_tma_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          GemmCfg<128, 2>::kSmemBytes + 64);
     attr_done[dev] = true;
@@ -442,7 +396,7 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
   } else {
     const int nj = (int)(N / 64);
     const int64_t tiles = total_tiles<2>(ni, nj, lower_only);
-    gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64 + kGemmExtraSmem, st>>>(
+    gemm_nt_tma_kernel<64, 2, 0><<<(unsigned)tiles, GemmCfg<64, 2>::kThreads, GemmCfg<64, 2>::kSmemBytes + 64, st>>>(
         ni, nj, K, A, lda, B, ldb, C, ldc, lower_only);
   }
 }

@@ -346,15 +346,15 @@ int cocons_dist_update(cocons_dist* c, int64_t K, const void* src, int64_t J_lo,
   const double* P = (const double*)src;
   if (J_lo <= K) J_lo = K + 1;
   if (J_hi > c->npanels) J_hi = c->npanels;
-  // Every update on the main stream by default.  Spreading the per-panel launches over up to three streams
-  // (COCONS_DIST_UPD_STREAMS=2|3) fills the tails (+7 % at 2 GPUs, 255 -> 264 TFLOP/s at 8) and reproduced the
-  // golden values, but tools/dist_repro.py then reported a false "not positive definite" on a repeated
-  // evaluation: like the overlapping contexts of tools/pool_stress.py, several large GEMM grids in flight at
-  // once are not reproducible yet (profiles/r01_reference_datasets_pool.md), so it stays an opt-in experiment.
+  // The per-panel launches of a step are independent: they are spread over three streams so that the tail of
+  // one launch is filled by the next (+7 % at 2 GPUs, 255 -> 264 TFLOP/s at 8 GPUs, n = 200 000).  Round 1 kept
+  // this opt-in because a repeated evaluation then reported a false "not positive definite"; that was the slot
+  // release race of the GEMM pipeline (csrc/chol.cu, fixed in round 2).  COCONS_DIST_UPD_STREAMS=1 puts every
+  // update back on the main stream.
   static int nstreams = -1;
   if (nstreams < 0) {
     const char* e = getenv("COCONS_DIST_UPD_STREAMS");
-    nstreams = e ? std::max(1, std::min(atoi(e), (int)cocons_dist::kUpdStreams)) : 1;
+    nstreams = e ? std::max(1, std::min(atoi(e), (int)cocons_dist::kUpdStreams)) : (int)cocons_dist::kUpdStreams;
   }
   int launched = 0;
   for (int64_t J = J_lo; J < J_hi; ++J) {

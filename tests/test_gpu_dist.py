@@ -27,9 +27,8 @@ def test_single_rank_distributed_path_matches_resident_context(name, n2ll_cases,
         for kind in (_lib.ML, _lib.PROFILE, _lib.REML):
             got = d.terms(kind, tl, c["limits"], tl["mean"])
             assert abs(got["logdet"] - ref[kind]["logdet"]) < 1e-11 * abs(ref[kind]["logdet"])
-            # the quadratic forms of the distributed solve are reproducible to ~5e-11 only (tools/dist_repro.py,
-            # open issue); the bar of the path is 1e-8
-            assert np.allclose(got["quad"], ref[kind]["quad"], rtol=1e-9, atol=0)
+            # two orchestrations of the same kernels: different blocking of the solve, so rounding-level agreement
+            assert np.allclose(got["quad"], ref[kind]["quad"], rtol=1e-10, atol=0)
             assert abs(got["logdet_w"] - ref[kind]["logdet_w"]) <= 1e-9 * max(1.0, abs(ref[kind]["logdet_w"]))
     # and the value against the committed golden
     n = c["n"]
@@ -58,4 +57,8 @@ def test_two_factorisation_drivers_agree_at_scale():
     with DistributedDenseLikelihood(locs, X, z) as d:
         b = d.terms(_lib.ML, bench.THETA, bench.LIMITS, bench.THETA["mean"])
     assert abs(a["logdet"] - b["logdet"]) < 1e-11 * abs(a["logdet"])
-    assert abs(a["quad"][0] - b["quad"][0]) < 1e-9 * abs(a["quad"][0])
+    assert abs(a["quad"][0] - b["quad"][0]) < 1e-10 * abs(a["quad"][0])
+    with DistributedDenseLikelihood(locs, X, z) as d:  # and the distributed driver is bit-reproducible
+        for _ in range(3):
+            c = d.terms(_lib.ML, bench.THETA, bench.LIMITS, bench.THETA["mean"])
+            assert c["logdet"] == b["logdet"] and c["quad"][0] == b["quad"][0]

@@ -159,9 +159,8 @@ def test_dmma_trailing_update_kernel_runs_at_speed():
 
 def test_pooled_evaluations_are_bit_identical_to_single_context(datasets):
     """Several evaluations submitted from host threads (DenseLikelihoodPool, the batched finite-difference
-    gradient of cocoOptim / getHessian) must give exactly the values a single context gives: the library
-    serialises the kernel chains of different contexts per device (tools/pool_stress.py found that
-    overlapping factorisations are not reproducible)."""
+    gradient of cocoOptim / getHessian) must give exactly the values a single context gives, although their
+    kernel chains overlap on the device (round 1 had to serialise them; see tests/test_gpu_repro.py)."""
     H = datasets["holes_training"]
     n = 3000
     X = cb.getScale(np.column_stack([np.ones(n), H[:n, 2], H[:n, 3]]))["std.covs"]
