@@ -678,10 +678,17 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     mod_DM = sc["std.covs"]
     n = coco_object.z.shape[0]
     lim = coco_object.info["smooth.limits"]
+    optim_type = optim_type.lower()  # R/optim.R:113
+    # every dense branch optimises with lambda = c(0, 0, lambda.reg) (R/optim.R:248, 287, 316) except the first
+    # step of the penalised two-step "ml" fit (:127-223: lambda.Sigma / lambda.betas > 0, then the model is pruned
+    # at sparse.point by .cocons.update.coco.first.step and refitted) - that caller-side model surgery is not
+    # mirrored: refuse rather than return a different optimum
     lam = (0.0, 0.0, coco_object.info["lambda.reg"])
-    if optim_type == "ml":
-        lam = (coco_object.info["lambda.Sigma"], coco_object.info["lambda.betas"], coco_object.info["lambda.reg"])
-    optim_type = optim_type.lower()
+    if optim_type == "ml" and coco_object.type == "dense" and (
+            coco_object.info.get("lambda.Sigma", 0) > 0 or coco_object.info.get("lambda.betas", 0) > 0):
+        raise NotImplementedError("cocoOptim(optim_type='ml') with lambda.Sigma / lambda.betas > 0 is the reference's "
+                                  "penalised two-step fit (R/optim.R:127-223), which is not mirrored; the penalised "
+                                  "objective itself is available through GetNeg2loglikelihood(lambda=...)")
     ctrl = {"maxiter": 500, "ftol": 1e-8, "maxcor": 100}  # R/profile.R:9-16 (factr, maxit, lmm)
     ctrl.update(optim_control or {})
     ndeps = ctrl.pop("ndeps", np.finfo(float).eps ** 0.25)

@@ -17,8 +17,8 @@ only.  `--check` verifies that claim bit for bit against one direct full call at
 The results are appended to tests/golden/n2ll_large.json with their provenance.
 """
 import argparse
-import ctypes
 import json
+import mmap
 import multiprocessing as mp
 import os
 import sys
@@ -67,7 +67,7 @@ def _block_pair(args):
 def assemble(theta, locs, X, block, workers):
     """Full covariance (lower triangle valid) in a shared buffer, by the reference's cov_rns on block pairs."""
     n = locs.shape[0]
-    S = mp.RawArray(ctypes.c_double, n * n)
+    S = mmap.mmap(-1, n * n * 8)  # anonymous shared mapping, inherited by the forked workers
     blocks = [np.arange(s, min(n, s + block)) for s in range(0, n, block)]
     _shared.update(S=S, n=n, blocks=blocks, theta=theta, locs=locs, X=X)
     pairs = [(a, b) for a in range(len(blocks)) for b in range(a, len(blocks))]

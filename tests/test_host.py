@@ -208,3 +208,17 @@ def test_taper_entry_points_validate_the_pattern_before_touching_a_device():
     with pytest.raises(ValueError, match="dense"):
         cb.coco("dense", {"a": np.zeros(3)}, locs, np.zeros(3), {"std.dev": "~ 1", "scale": "~ 1"},
                 info={"taper": cb.cov_wend1, "delta": 0.1})
+
+
+def test_cocooptim_ml_follows_the_reference_penalty_layout(datasets):
+    """R/optim.R:113 lower-cases optim.type before anything else; :127 sends lambda.Sigma / lambda.betas > 0
+    with 'ml' into the penalised two-step fit, which is not mirrored: refused before any device call,
+    whatever the case of the type string."""
+    H = datasets["holes_training"][:40]
+    data = {"x": H[:, 0], "y": H[:, 1], "cov_x": H[:, 2], "cov_y": H[:, 3]}
+    ml = {"mean": 0, "std.dev": "~ 1 + cov_x", "scale": "~ 1", "aniso": 0, "tilt": 0, "smooth": 1.5, "nugget": -np.inf}
+    bounds = {"theta_init": np.zeros(3), "theta_lower": -3 * np.ones(3), "theta_upper": 3 * np.ones(3)}
+    for kind in ("ml", "ML"):
+        obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml, info={"lambda.Sigma": 0.1})
+        with pytest.raises(NotImplementedError, match="two-step"):
+            cb.cocoOptim(obj, bounds, optim_type=kind)
