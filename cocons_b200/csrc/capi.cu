@@ -423,6 +423,7 @@ void cocons_ctx_destroy(cocons_ctx* c) {
   cudaFree(c->dX), cudaFree(c->dLocs), cudaFree(c->dZ), cudaFree(c->dXb), cudaFree(c->dTheta), cudaFree(c->dSite);
   cudaFree(c->dOrig), cudaFree(c->dA), cudaFree(c->dRhs);
   cudaFree(c->dTapCol), cudaFree(c->dTapRow), cudaFree(c->dInv), cudaFree(c->dTap), cudaFree(c->dCheck);
+  solve_workspace_destroy(&c->ws);
   chol_workspace_destroy(&c->ws);
   cudaFree(c->dGram);
   if (c->hStage) cudaFreeHost(c->hStage);
@@ -473,7 +474,7 @@ int cocons_ctx_create(int device, int64_t n, int64_t p, int64_t r, const double*
   CTX_TRY(cudaMalloc(&c->dSite, sizeof(double) * SF_COUNT * np));
   CTX_TRY(cudaMalloc(&c->dOrig, sizeof(int) * np));
   CTX_TRY(cudaMalloc(&c->dA, sizeof(double) * np * np));
-  if (chol_workspace_create(np, &c->ws) != 0) {
+  if (chol_workspace_create(np, &c->ws) != 0 || solve_workspace_create(np, &c->ws) != 0) {
     set_error("ctx_create: out of device memory for the factorisation workspace");
     cocons_ctx_destroy(c);
     return COCONS_ERR_ALLOC;
@@ -613,7 +614,7 @@ static int n2ll_impl(cocons_ctx* c, int kind, const double* theta6, const double
   if (qx > 0) {
     const double* src = (kind == COCONS_PROFILE) ? c->dXb : c->dX;
     COCONS_CUDA_TRY(cudaMemcpyAsync(c->dRhs, src, sizeof(double) * np * qx, cudaMemcpyDeviceToDevice, st));
-    forward_solve(c->dA, np, np, c->ws.winv, c->dRhs, np, qx, st);
+    forward_solve_ws(c->dA, np, np, c->ws, c->dRhs, np, qx, st);
   }
   const int chunk = kMaxRhs - qx;
   double lw = 0.0;
@@ -624,7 +625,7 @@ static int n2ll_impl(cocons_ctx* c, int kind, const double* theta6, const double
     residual_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(c->n, np, (int)p, nc, c->dX, c->dZ + c0 * np,
                                                                   kind == COCONS_ML ? c->dTheta + 6 * p : nullptr,
                                                                   rhs);
-    forward_solve(c->dA, np, np, c->ws.winv, rhs, np, nc, st);
+    forward_solve_ws(c->dA, np, np, c->ws, rhs, np, nc, st);
     const int k = qx + nc;
     launch_gram(c->dRhs, c->n, np, k, c->dGram, st);
     if (c0 + nc >= c->r) COCONS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
@@ -840,7 +841,7 @@ int cocons_profile_betas(cocons_ctx* c, int kind, double* betas) {
   cudaStream_t st = c->stream;
   const double* src = (kind == COCONS_PROFILE) ? c->dXb : c->dX;
   COCONS_CUDA_TRY(cudaMemcpyAsync(c->dRhs, src, sizeof(double) * np * qx, cudaMemcpyDeviceToDevice, st));
-  forward_solve(c->dA, np, np, c->ws.winv, c->dRhs, np, qx, st);
+  forward_solve_ws(c->dA, np, np, c->ws, c->dRhs, np, qx, st);
   // rowSums(z)/r as one right-hand side (R/optim.R:341)
   std::vector<double> zsum((size_t)np, 0.0), hz((size_t)np * c->r);
   COCONS_CUDA_TRY(cudaMemcpyAsync(hz.data(), c->dZ, sizeof(double) * np * c->r, cudaMemcpyDeviceToHost, st));
@@ -849,7 +850,7 @@ int cocons_profile_betas(cocons_ctx* c, int kind, double* betas) {
     for (int64_t i = 0; i < c->n; ++i) zsum[(size_t)i] += hz[(size_t)col * np + i];
   double* rhs = c->dRhs + (int64_t)qx * np;
   COCONS_CUDA_TRY(cudaMemcpyAsync(rhs, zsum.data(), sizeof(double) * np, cudaMemcpyHostToDevice, st));
-  forward_solve(c->dA, np, np, c->ws.winv, rhs, np, 1, st);
+  forward_solve_ws(c->dA, np, np, c->ws, rhs, np, 1, st);
   const int k = qx + 1;
   launch_gram(c->dRhs, c->n, np, k, c->dGram, st);
   double* hG = c->hStage + 7 * c->p;
@@ -1012,7 +1013,7 @@ static int predict_impl(cocons_ctx* c, int64_t m, const double* locs_pred, const
     for (int64_t s = 0; s < c->n; ++s) hr[(size_t)s] = resid[c->perm[(size_t)s]];
     COCONS_CUDA_TRY(cudaMemcpyAsync(c->dRhs, hr.data(), sizeof(double) * np, cudaMemcpyHostToDevice, st));
     COCONS_CUDA_TRY(cudaStreamSynchronize(st));
-    forward_solve(c->dA, np, np, c->ws.winv, c->dRhs, np, 1, st);
+    forward_solve_ws(c->dA, np, np, c->ws, c->dRhs, np, 1, st);
   }
   const int64_t mc_max = std::min<int64_t>(round_up(m, kTile), 4096);
   PredBlock blk;

@@ -107,7 +107,14 @@ struct CholWorkspace {
   cudaStream_t panel_stream;  // high-priority side stream for the look-ahead panel
   cudaEvent_t ev_a, ev_p;
   cudaEvent_t ev_k0, ev_k1;  // bracket the largest trailing-update launch (roofline measurement)
+  // dataflow forward substitution (solve.cu, solve_workspace_create): control words, work-unit table, partial sums
+  unsigned* solve_ctrl;   // [0] ticket, [1] front (rows of Y finished), [2] error, [4 + I] finished partial units of row I
+  int* solve_units;       // 4 ints per unit: tile row I, first tile column J0, end J1, chunk index
+  double* solve_part;     // (I * solve_nchunks + chunk) * kSolveMaxRhs * kTile doubles
+  int solve_nunits, solve_nchunks;
 };
+constexpr int kSolveMaxRhs = 8;   // right-hand sides per launch of the substitution kernels
+constexpr int kSolveChunk = 16;   // tile columns per work unit (2 MB of L)
 int chol_workspace_create(int64_t n_pad, CholWorkspace* ws);
 void chol_workspace_destroy(CholWorkspace* ws);
 // tiles [J0, J0+jb) of one outer panel (potrf + panel solve + in-panel update) on stream st; A is the
@@ -123,6 +130,12 @@ void launch_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, 
 void launch_logdet(const double* L, int64_t n, int64_t ld, double* out, cudaStream_t st);
 void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* winv, double* B, int64_t ldb, int nrhs,
                    cudaStream_t st);
+int solve_workspace_create(int64_t n_pad, CholWorkspace* ws);
+void solve_workspace_destroy(CholWorkspace* ws);
+// L Y = B with the dataflow kernel when ws carries a solve workspace (else the cooperative kernel above); a
+// stalled dependency wait (which would be a bug) is reported through *info_dev = COCONS_ERR_CUDA instead of hanging
+void forward_solve_ws(const double* L, int64_t n_pad, int64_t ld, const CholWorkspace& ws, double* B, int64_t ldb,
+                      int nrhs, cudaStream_t st);
 void launch_gram(const double* Y, int64_t n, int64_t ldy, int k, double* G, cudaStream_t st);
 
 }  // namespace cocons

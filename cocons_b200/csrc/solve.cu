@@ -8,6 +8,9 @@
 // right-hand sides (4 n^2 bytes).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "../../include/cocons_b200.h"
 #include "common.cuh"
 
@@ -256,6 +259,282 @@ void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* win
       launch_fwd_coop<8>(L, ld, winv, Bc, Yc, ldb, nt, nr, st);
   }
   cudaMemcpyAsync(B, Y, sizeof(double) * (size_t)nrhs * (size_t)ldb, cudaMemcpyDeviceToDevice, st);
+}
+
+// ---------------------------------------------------------------------------
+// Dataflow forward substitution (K6b, the default).  The cooperative kernel above pays one grid barrier per
+// 128-row step (391 of them at n = 50 000: 7.7 ms against a 1.5 ms HBM floor).  Here the work is cut into
+// UNITS - tile row I times a chunk of up to kSolveChunk tile columns [J0, J1), 2 MB of L - handed out through
+// a ticket counter to persistent CTAs, and the only synchronisation is the dependency itself:
+//   ctrl[1] = front = number of finished tile rows of Y (y_I needs y_{I-1}, so rows finish in order)
+//   a unit may consume tile column J once front > J; it accumulates  sum_J L_IJ y_J  for its chunk
+//   the unit holding the LAST chunk of row I (J1 == I) adds the partial sums of the row's other chunks in chunk
+//   order (a fixed order: results do not depend on the schedule), forms y_I = W_I (b_I - sum), stores it over
+//   b_I, and publishes front = I + 1.
+// Units are issued in the order of the front value they need (J1), last-chunk units first among equals: every
+// unit waits only for units with SMALLER tickets, which are already running or done - no deadlock for any
+// number of resident CTAs, so an ordinary launch suffices.  CTAs far behind the front stream L at full
+// bandwidth; the chain front -> L_{I,I-1} y_{I-1} -> W_I t -> front (two 128 x 128 products out of L2,
+// prefetched) is the critical path.  A dependency wait that does not end (a bug) sets ctrl[2] and ends the
+// kernel instead of hanging the device.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr unsigned kSolveSpinLimit = 1u << 25;  // ~seconds; a healthy wait ends within microseconds
+constexpr int kSolveSub = 4;                     // tile columns whose y is staged in shared memory at a time
+
+template <int NR>
+__global__ void __launch_bounds__(256, 2)
+    fwd_solve_flow_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Winv, double* B,
+                          int64_t ldb, int nr, unsigned* ctrl, const int* __restrict__ units, unsigned nunits,
+                          double* part, int nchunks, int* info) {
+  extern __shared__ __align__(16) double fsm[];
+  double(*ysm)[kSolveSub * kTile] = reinterpret_cast<double(*)[kSolveSub * kTile]>(fsm);
+  double(*red)[256] = reinterpret_cast<double(*)[256]>(fsm + NR * kSolveSub * kTile);
+  __shared__ unsigned s_u, s_val;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, row = tid & (kTile - 1), h = tid >> 7;
+  unsigned front_seen = 0;  // uniform over the CTA
+
+  // thread 0 polls *word until it is >= need; everybody gets the value seen.  false = gave up (error raised)
+  auto wait_for = [&](const unsigned* word, unsigned need, unsigned& seen) -> bool {
+    if (tid == 0) {
+      unsigned v = ld_acquire_u32(word), spins = 0;
+      int bad = 0;
+      while (v < need) {
+        if (++spins > 64) __nanosleep(32);
+        if ((spins & 1023u) == 0 && (spins > kSolveSpinLimit || ld_acquire_u32(ctrl + 2) != 0)) {
+          bad = 1;
+          break;
+        }
+        v = ld_acquire_u32(word);
+      }
+      if (bad) {
+        atomicExch(ctrl + 2, 1u);
+        atomicCAS(info, 0, COCONS_ERR_CUDA);
+      }
+      s_val = v, s_bad = bad;
+    }
+    __syncthreads();
+    const bool ok = (s_bad == 0);
+    seen = s_val;
+    __syncthreads();  // s_val / s_bad may be rewritten by the next wait
+    return ok;
+  };
+
+  for (;;) {
+    if (tid == 0) s_u = atomicAdd(ctrl, 1u);
+    __syncthreads();
+    const unsigned u = s_u;
+    __syncthreads();
+    if (u >= nunits) break;
+    const int I = units[4 * u], J0 = units[4 * u + 1], J1 = units[4 * u + 2], ch = units[4 * u + 3];
+    const bool is_final = (J1 == I);
+    const int64_t i0 = (int64_t)I * kTile;
+    const double* W = Winv + (int64_t)I * kTile * kTile;
+    if (is_final) {  // the two tiles of the critical path towards L2: W_I and L_{I,I-1} (128 KB each, 128 B lines)
+      for (int l = tid; l < kTile * 8; l += 256) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (int64_t)l * 16));
+        if (I > 0)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(L + ((int64_t)(I - 1) * kTile + (l >> 3)) * ld + i0 + (l & 7) * 16));
+      }
+    }
+    double acc[NR], pre[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = 0.0, pre[c] = 0.0;
+    bool presummed = false;
+    // partial sums of the row's earlier chunks, in chunk order (tid < 128 holds row `tid`)
+    auto presum = [&]() -> bool {
+      unsigned done;
+      if (ch > 0 && !wait_for(ctrl + 4 + I, (unsigned)ch, done)) return false;
+      if (tid < kTile)
+        for (int cc = 0; cc < ch; ++cc) {
+          const double* pp = part + ((int64_t)I * nchunks + cc) * kSolveMaxRhs * kTile + tid;
+#pragma unroll
+          for (int c = 0; c < NR; ++c) pre[c] += __ldcg(pp + c * kTile);
+        }
+      presummed = true;
+      return true;
+    };
+
+    int ja = J0;
+    while (ja < J1) {
+      const int avail = ((int)front_seen < J1) ? (int)front_seen : J1;
+      if (avail <= ja) {  // nothing consumable yet: use the wait (last-chunk units), then poll the front
+        if (is_final && !presummed && !presum()) return;
+        unsigned f;
+        if (!wait_for(ctrl + 1, (unsigned)ja + 1, f)) return;
+        front_seen = f > front_seen ? f : front_seen;
+        continue;
+      }
+      const int jb = (ja + kSolveSub < avail) ? ja + kSolveSub : avail, nt = jb - ja;
+      for (int idx = tid; idx < NR * nt * kTile; idx += 256) {
+        const int c = idx / (nt * kTile), k = idx - c * nt * kTile;
+        ysm[c][k] = (c < nr) ? __ldcg(B + (int64_t)c * ldb + (int64_t)ja * kTile + k) : 0.0;
+      }
+      __syncthreads();
+      for (int t = 0; t < nt; ++t) {
+        const double* Lp = L + ((int64_t)(ja + t) * kTile + h * (kTile / 2)) * ld + i0 + row;
+        const double* yp = &ysm[0][t * kTile + h * (kTile / 2)];
+#pragma unroll 16
+        for (int k = 0; k < kTile / 2; ++k) {
+          const double l = __ldg(Lp + (int64_t)k * ld);
+#pragma unroll
+          for (int c = 0; c < NR; ++c) acc[c] = fma(l, yp[c * kSolveSub * kTile + k], acc[c]);
+        }
+      }
+      __syncthreads();  // ysm is rewritten by the next range
+      ja = jb;
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) red[c][tid] = acc[c];
+    __syncthreads();
+    if (!is_final) {
+      if (tid < kTile) {
+        double* pp = part + ((int64_t)I * nchunks + ch) * kSolveMaxRhs * kTile + tid;
+#pragma unroll
+        for (int c = 0; c < NR; ++c) pp[c * kTile] = red[c][tid] + red[c][tid + kTile];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(ctrl + 4 + I, 1u);
+      }
+      continue;
+    }
+    if (!presummed && !presum()) return;
+    if (tid < kTile) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        const double own = red[c][tid] + red[c][tid + kTile];
+        const double b = (c < nr) ? __ldcg(B + (int64_t)c * ldb + i0 + tid) : 0.0;
+        ysm[c][tid] = b - (pre[c] + own);
+      }
+    }
+    __syncthreads();
+    {  // y_I = W_I t: thread (row, h) sums half of the k range of its row (W has explicit zeros above the diagonal)
+      double w[NR];
+#pragma unroll
+      for (int c = 0; c < NR; ++c) w[c] = 0.0;
+      const double* Wp = W + (int64_t)h * (kTile / 2) * kTile + row;
+#pragma unroll 16
+      for (int k = 0; k < kTile / 2; ++k) {
+        const double x = __ldg(Wp + (int64_t)k * kTile);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) w[c] = fma(x, ysm[c][h * (kTile / 2) + k], w[c]);
+      }
+      __syncthreads();  // red is still being read above by tid < 128
+#pragma unroll
+      for (int c = 0; c < NR; ++c) red[c][tid] = w[c];
+    }
+    __syncthreads();
+    if (tid < kTile) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c)
+        if (c < nr) B[(int64_t)c * ldb + i0 + tid] = red[c][tid] + red[c][tid + kTile];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release_u32(ctrl + 1, (unsigned)I + 1);
+    }
+    if (front_seen < (unsigned)I + 1) front_seen = (unsigned)I + 1;
+  }
+}
+
+int solve_workspace_create(int64_t n_pad, CholWorkspace* ws) {
+  const int T = (int)(n_pad / kTile);
+  const int nchunks = (T - 1 + kSolveChunk - 1) / kSolveChunk > 0 ? (T - 1 + kSolveChunk - 1) / kSolveChunk : 1;
+  struct Unit {
+    int I, J0, J1, ch;
+  };
+  std::vector<Unit> units;
+  units.push_back({0, 0, 0, 0});
+  for (int I = 1; I < T; ++I)
+    for (int ch = 0; ch * kSolveChunk < I; ++ch)
+      units.push_back({I, ch * kSolveChunk, std::min((ch + 1) * kSolveChunk, I), ch});
+  // issue order: by the front value a unit needs (J1); among equals the row-finishing units first, then by row
+  std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) {
+    if (a.J1 != b.J1) return a.J1 < b.J1;
+    const bool fa = a.J1 == a.I, fb = b.J1 == b.I;
+    if (fa != fb) return fa;
+    return a.I < b.I;
+  });
+  ws->solve_nunits = (int)units.size(), ws->solve_nchunks = nchunks;
+  if (cudaMalloc(&ws->solve_ctrl, sizeof(unsigned) * (4 + (size_t)T)) != cudaSuccess ||
+      cudaMalloc(&ws->solve_units, sizeof(int) * 4 * units.size()) != cudaSuccess ||
+      cudaMalloc(&ws->solve_part, sizeof(double) * (size_t)T * nchunks * kSolveMaxRhs * kTile) != cudaSuccess) {
+    solve_workspace_destroy(ws);
+    return COCONS_ERR_ALLOC;
+  }
+  if (cudaMemcpy(ws->solve_units, units.data(), sizeof(int) * 4 * units.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    solve_workspace_destroy(ws);
+    return COCONS_ERR_CUDA;
+  }
+  return 0;
+}
+
+void solve_workspace_destroy(CholWorkspace* ws) {
+  cudaFree(ws->solve_ctrl), cudaFree(ws->solve_units), cudaFree(ws->solve_part);
+  ws->solve_ctrl = nullptr, ws->solve_units = nullptr, ws->solve_part = nullptr, ws->solve_nunits = 0;
+}
+
+template <int NR>
+static void launch_fwd_flow(const double* L, int64_t ld, const CholWorkspace& ws, double* B, int64_t ldb, int nr,
+                            int64_t T, cudaStream_t st) {
+  static int sms[16] = {};
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  constexpr int kSmem = NR * (kSolveSub * kTile + 256) * (int)sizeof(double);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(fwd_solve_flow_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    attr_done[dev] = true;
+  }
+  const int nsm = (dev < 16 && sms[dev] > 0) ? sms[dev] : 148;
+  const unsigned grid = (unsigned)std::min<int64_t>(ws.solve_nunits, 2 * (int64_t)nsm);
+  cudaMemsetAsync(ws.solve_ctrl, 0, sizeof(unsigned) * (4 + (size_t)T), st);
+  note_launch();
+  fwd_solve_flow_kernel<NR><<<grid, 256, kSmem, st>>>(L, ld, ws.winv, B, ldb, nr, ws.solve_ctrl, ws.solve_units,
+                                                      (unsigned)ws.solve_nunits, ws.solve_part, ws.solve_nchunks,
+                                                      ws.info);
+}
+
+static bool solve_uses_flow() {
+  static int flow = -1;
+  if (flow < 0) {
+    const char* e = getenv("COCONS_SOLVE_FLOW");  // 0: the cooperative kernel (K6) instead of the dataflow kernel (K6b)
+    flow = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return flow != 0;
+}
+
+void forward_solve_ws(const double* L, int64_t n_pad, int64_t ld, const CholWorkspace& ws, double* B, int64_t ldb,
+                      int nrhs, cudaStream_t st) {
+  if (!ws.solve_units || !solve_uses_flow()) {
+    forward_solve(L, n_pad, ld, ws.winv, B, ldb, nrhs, st);
+    return;
+  }
+  const int64_t T = n_pad / kTile;
+  for (int c0 = 0; c0 < nrhs; c0 += kSolveMaxRhs) {
+    const int nr = (nrhs - c0 < kSolveMaxRhs) ? nrhs - c0 : kSolveMaxRhs;
+    double* Bc = B + (int64_t)c0 * ldb;
+    if (nr == 1)
+      launch_fwd_flow<1>(L, ld, ws, Bc, ldb, nr, T, st);
+    else if (nr == 2)
+      launch_fwd_flow<2>(L, ld, ws, Bc, ldb, nr, T, st);
+    else if (nr <= 4)
+      launch_fwd_flow<4>(L, ld, ws, Bc, ldb, nr, T, st);
+    else
+      launch_fwd_flow<8>(L, ld, ws, Bc, ldb, nr, T, st);
+  }
 }
 
 // ---------------------------------------------------------------------------
