@@ -289,19 +289,32 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 constexpr unsigned kSolveSpinLimit = 1u << 25;  // ~seconds; a healthy wait ends within microseconds
 constexpr int kSolveSub = 4;                     // tile columns whose y is staged in shared memory at a time
 
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr unsigned long long kSolveUnset = ~0ull;  // cudaMemset(0xFF): no arithmetic result has this bit pattern
+
 template <int NR>
-__global__ void __launch_bounds__(256, 2)
-    fwd_solve_flow_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Winv, double* B,
+__global__ void __launch_bounds__(256, (NR == 1) ? 2 : 1)
+    fwd_solve_flow_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Winv, double* B, double* Y,
                           int64_t ldb, int nr, unsigned* ctrl, const int* __restrict__ units, unsigned nunits,
                           double* part, int nchunks, int* info) {
   extern __shared__ __align__(16) double fsm[];
-  double(*ysm)[kSolveSub * kTile] = reinterpret_cast<double(*)[kSolveSub * kTile]>(fsm);
-  double(*red)[256] = reinterpret_cast<double(*)[256]>(fsm + NR * kSolveSub * kTile);
+  double(*ysm)[kSolveSub * kTile] = reinterpret_cast<double(*)[kSolveSub * kTile]>(fsm);  // staged y / t
+  double(*red)[256] = reinterpret_cast<double(*)[256]>(fsm + NR * kSolveSub * kTile);      // (row, half) partials
+  double(*rq)[4][kTile] = reinterpret_cast<double(*)[4][kTile]>(fsm + NR * (kSolveSub * kTile + 256));  // quarters
   __shared__ unsigned s_u, s_val;
   __shared__ int s_bad;
   const int tid = threadIdx.x, row = tid & (kTile - 1), h = tid >> 7;
-  unsigned front_seen = 0;  // uniform over the CTA
+  const int rp = tid & 63, kq = tid >> 6;  // critical-path products: rows 2 rp, 2 rp + 1, columns [32 kq, 32 kq + 32)
+  unsigned front_seen = 0;                 // uniform over the CTA
 
+  auto give_up = [&]() {
+    atomicExch(ctrl + 2, 1u);
+    atomicCAS(info, 0, COCONS_ERR_CUDA);
+  };
   // thread 0 polls *word until it is >= need; everybody gets the value seen.  false = gave up (error raised)
   auto wait_for = [&](const unsigned* word, unsigned need, unsigned& seen) -> bool {
     if (tid == 0) {
@@ -315,10 +328,7 @@ __global__ void __launch_bounds__(256, 2)
         }
         v = ld_acquire_u32(word);
       }
-      if (bad) {
-        atomicExch(ctrl + 2, 1u);
-        atomicCAS(info, 0, COCONS_ERR_CUDA);
-      }
+      if (bad) give_up();
       s_val = v, s_bad = bad;
     }
     __syncthreads();
@@ -363,10 +373,13 @@ __global__ void __launch_bounds__(256, 2)
       return true;
     };
 
+    // ---- streaming part: tile columns [J0, Js) as the front releases them.  The last tile column of a
+    //      row-finishing unit (J = I - 1, the one the front is waiting for) takes the fast path below.
+    const int Js = (is_final && I > 0) ? I - 1 : J1;
     int ja = J0;
-    while (ja < J1) {
-      const int avail = ((int)front_seen < J1) ? (int)front_seen : J1;
-      if (avail <= ja) {  // nothing consumable yet: use the wait (last-chunk units), then poll the front
+    while (ja < Js) {
+      const int avail = ((int)front_seen < Js) ? (int)front_seen : Js;
+      if (avail <= ja) {  // nothing consumable yet: use the wait (row-finishing units), then poll the front
         if (is_final && !presummed && !presum()) return;
         unsigned f;
         if (!wait_for(ctrl + 1, (unsigned)ja + 1, f)) return;
@@ -376,17 +389,36 @@ __global__ void __launch_bounds__(256, 2)
       const int jb = (ja + kSolveSub < avail) ? ja + kSolveSub : avail, nt = jb - ja;
       for (int idx = tid; idx < NR * nt * kTile; idx += 256) {
         const int c = idx / (nt * kTile), k = idx - c * nt * kTile;
-        ysm[c][k] = (c < nr) ? __ldcg(B + (int64_t)c * ldb + (int64_t)ja * kTile + k) : 0.0;
+        ysm[c][k] = (c < nr) ? __ldcg(Y + (int64_t)c * ldb + (int64_t)ja * kTile + k) : 0.0;
       }
       __syncthreads();
-      for (int t = 0; t < nt; ++t) {
-        const double* Lp = L + ((int64_t)(ja + t) * kTile + h * (kTile / 2)) * ld + i0 + row;
-        const double* yp = &ysm[0][t * kTile + h * (kTile / 2)];
-#pragma unroll 16
-        for (int k = 0; k < kTile / 2; ++k) {
-          const double l = __ldg(Lp + (int64_t)k * ld);
+      {  // 4 nt batches of 16 columns per thread, the next batch in flight while the current one is consumed
+        const int nb = 4 * nt;
+        auto src = [&](int q) { return L + ((int64_t)(ja + (q >> 2)) * kTile + h * (kTile / 2) + (q & 3) * 16) * ld + i0 + row; };
+        auto use = [&](const double(&v)[16], int q) {
+          const double* yp = &ysm[0][(q >> 2) * kTile + h * (kTile / 2) + (q & 3) * 16];
 #pragma unroll
-          for (int c = 0; c < NR; ++c) acc[c] = fma(l, yp[c * kSolveSub * kTile + k], acc[c]);
+          for (int k = 0; k < 16; ++k)
+#pragma unroll
+            for (int c = 0; c < NR; ++c) acc[c] = fma(v[k], yp[c * kSolveSub * kTile + k], acc[c]);
+        };
+        double va[16], vb[16];
+        {
+          const double* p0 = src(0);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) va[k] = __ldg(p0 + (int64_t)k * ld);
+        }
+        for (int q = 0; q < nb; q += 2) {  // nb is even
+          const double* p1 = src(q + 1);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) vb[k] = __ldg(p1 + (int64_t)k * ld);
+          use(va, q);
+          if (q + 2 < nb) {
+            const double* p2 = src(q + 2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) va[k] = __ldg(p2 + (int64_t)k * ld);
+          }
+          use(vb, q + 1);
         }
       }
       __syncthreads();  // ysm is rewritten by the next range
@@ -394,8 +426,8 @@ __global__ void __launch_bounds__(256, 2)
     }
 #pragma unroll
     for (int c = 0; c < NR; ++c) red[c][tid] = acc[c];
-    __syncthreads();
     if (!is_final) {
+      __syncthreads();
       if (tid < kTile) {
         double* pp = part + ((int64_t)I * nchunks + ch) * kSolveMaxRhs * kTile + tid;
 #pragma unroll
@@ -408,36 +440,92 @@ __global__ void __launch_bounds__(256, 2)
       }
       continue;
     }
+    // ---- row-finishing unit: everything that does not depend on y_{I-1} first
     if (!presummed && !presum()) return;
+    double q0[NR], q1[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) q0[c] = q1[c] = 0.0;
+    if (I > 0) {
+      double2 lreg[32];  // this thread's piece of L_{I,I-1}, in registers before the front gets here
+      const double* Lp = L + ((int64_t)(I - 1) * kTile + 32 * kq) * ld + i0 + 2 * rp;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) lreg[k] = __ldg(reinterpret_cast<const double2*>(Lp + (int64_t)k * ld));
+      // y_{I-1}, element by element as its owner stores it (Y was filled with the 'unset' pattern): one hop
+      // instead of a flag round trip followed by a data round trip
+      int bad = 0;
+      for (int idx = tid; idx < NR * kTile; idx += 256) {
+        const int c = idx >> 7, k = idx & (kTile - 1);
+        double v = 0.0;
+        if (c < nr) {
+          const double* yp = Y + (int64_t)c * ldb + (int64_t)(I - 1) * kTile + k;
+          unsigned long long bits = ld_relaxed_u64(yp);
+          unsigned spins = 0;
+          while (bits == kSolveUnset) {
+            if ((++spins & 1023u) == 0 && (spins > kSolveSpinLimit || ld_acquire_u32(ctrl + 2) != 0)) {
+              bad = 1;
+              break;
+            }
+            bits = ld_relaxed_u64(yp);
+          }
+          v = __longlong_as_double((long long)bits);
+        }
+        ysm[c][k] = v;
+      }
+      if (__syncthreads_or(bad)) {
+        if (tid == 0) give_up();
+        return;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          const double y = ysm[c][32 * kq + k];
+          q0[c] = fma(lreg[k].x, y, q0[c]);
+          q1[c] = fma(lreg[k].y, y, q1[c]);
+        }
+    }
+    asm volatile("" ::: "memory");  // keep the W loads behind the products above (lreg and wreg never live together)
+    double2 wreg[32];  // W_I from L2 (prefetched at the start of the unit), in flight during the reduction below
+    {
+      const double* Wp = W + (int64_t)(32 * kq) * kTile + 2 * rp;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) wreg[k] = __ldg(reinterpret_cast<const double2*>(Wp + (int64_t)k * kTile));
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) rq[c][kq][2 * rp] = q0[c], rq[c][kq][2 * rp + 1] = q1[c];
+    __syncthreads();
     if (tid < kTile) {
 #pragma unroll
       for (int c = 0; c < NR; ++c) {
         const double own = red[c][tid] + red[c][tid + kTile];
+        const double last = (rq[c][0][tid] + rq[c][1][tid]) + (rq[c][2][tid] + rq[c][3][tid]);
         const double b = (c < nr) ? __ldcg(B + (int64_t)c * ldb + i0 + tid) : 0.0;
-        ysm[c][tid] = b - (pre[c] + own);
+        ysm[c][tid] = b - ((pre[c] + own) + last);
       }
     }
     __syncthreads();
-    {  // y_I = W_I t: thread (row, h) sums half of the k range of its row (W has explicit zeros above the diagonal)
-      double w[NR];
+    // y_I = W_I t (W has explicit zeros above the diagonal)
 #pragma unroll
-      for (int c = 0; c < NR; ++c) w[c] = 0.0;
-      const double* Wp = W + (int64_t)h * (kTile / 2) * kTile + row;
-#pragma unroll 16
-      for (int k = 0; k < kTile / 2; ++k) {
-        const double x = __ldg(Wp + (int64_t)k * kTile);
+    for (int c = 0; c < NR; ++c) q0[c] = q1[c] = 0.0;
 #pragma unroll
-        for (int c = 0; c < NR; ++c) w[c] = fma(x, ysm[c][h * (kTile / 2) + k], w[c]);
+    for (int k = 0; k < 32; ++k)
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        const double t = ysm[c][32 * kq + k];
+        q0[c] = fma(wreg[k].x, t, q0[c]);
+        q1[c] = fma(wreg[k].y, t, q1[c]);
       }
-      __syncthreads();  // red is still being read above by tid < 128
 #pragma unroll
-      for (int c = 0; c < NR; ++c) red[c][tid] = w[c];
-    }
+    for (int c = 0; c < NR; ++c) rq[c][kq][2 * rp] = q0[c], rq[c][kq][2 * rp + 1] = q1[c];
     __syncthreads();
     if (tid < kTile) {
 #pragma unroll
       for (int c = 0; c < NR; ++c)
-        if (c < nr) B[(int64_t)c * ldb + i0 + tid] = red[c][tid] + red[c][tid + kTile];
+        if (c < nr) {
+          const double y = (rq[c][0][tid] + rq[c][1][tid]) + (rq[c][2][tid] + rq[c][3][tid]);
+          Y[(int64_t)c * ldb + i0 + tid] = y;  // what the other units read
+          B[(int64_t)c * ldb + i0 + tid] = y;  // the caller's result, in place of b_I
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -486,13 +574,13 @@ void solve_workspace_destroy(CholWorkspace* ws) {
 }
 
 template <int NR>
-static void launch_fwd_flow(const double* L, int64_t ld, const CholWorkspace& ws, double* B, int64_t ldb, int nr,
-                            int64_t T, cudaStream_t st) {
+static void launch_fwd_flow(const double* L, int64_t ld, const CholWorkspace& ws, double* B, double* Y, int64_t ldb,
+                            int nr, int64_t T, cudaStream_t st) {
   static int sms[16] = {};
   static bool attr_done[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  constexpr int kSmem = NR * (kSolveSub * kTile + 256) * (int)sizeof(double);
+  constexpr int kSmem = NR * (kSolveSub * kTile + 256 + 4 * kTile) * (int)sizeof(double);
   if (dev < 16 && !attr_done[dev]) {
     cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(fwd_solve_flow_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -501,8 +589,9 @@ static void launch_fwd_flow(const double* L, int64_t ld, const CholWorkspace& ws
   const int nsm = (dev < 16 && sms[dev] > 0) ? sms[dev] : 148;
   const unsigned grid = (unsigned)std::min<int64_t>(ws.solve_nunits, 2 * (int64_t)nsm);
   cudaMemsetAsync(ws.solve_ctrl, 0, sizeof(unsigned) * (4 + (size_t)T), st);
+  cudaMemsetAsync(Y, 0xFF, sizeof(double) * (size_t)nr * (size_t)ldb, st);  // every y 'unset' (kSolveUnset)
   note_launch();
-  fwd_solve_flow_kernel<NR><<<grid, 256, kSmem, st>>>(L, ld, ws.winv, B, ldb, nr, ws.solve_ctrl, ws.solve_units,
+  fwd_solve_flow_kernel<NR><<<grid, 256, kSmem, st>>>(L, ld, ws.winv, B, Y, ldb, nr, ws.solve_ctrl, ws.solve_units,
                                                       (unsigned)ws.solve_nunits, ws.solve_part, ws.solve_nchunks,
                                                       ws.info);
 }
@@ -523,17 +612,19 @@ void forward_solve_ws(const double* L, int64_t n_pad, int64_t ld, const CholWork
     return;
   }
   const int64_t T = n_pad / kTile;
+  double* Y = B + (int64_t)nrhs * ldb;  // scratch behind the right-hand sides (same contract as forward_solve)
   for (int c0 = 0; c0 < nrhs; c0 += kSolveMaxRhs) {
     const int nr = (nrhs - c0 < kSolveMaxRhs) ? nrhs - c0 : kSolveMaxRhs;
     double* Bc = B + (int64_t)c0 * ldb;
+    double* Yc = Y + (int64_t)c0 * ldb;
     if (nr == 1)
-      launch_fwd_flow<1>(L, ld, ws, Bc, ldb, nr, T, st);
+      launch_fwd_flow<1>(L, ld, ws, Bc, Yc, ldb, nr, T, st);
     else if (nr == 2)
-      launch_fwd_flow<2>(L, ld, ws, Bc, ldb, nr, T, st);
+      launch_fwd_flow<2>(L, ld, ws, Bc, Yc, ldb, nr, T, st);
     else if (nr <= 4)
-      launch_fwd_flow<4>(L, ld, ws, Bc, ldb, nr, T, st);
+      launch_fwd_flow<4>(L, ld, ws, Bc, Yc, ldb, nr, T, st);
     else
-      launch_fwd_flow<8>(L, ld, ws, Bc, ldb, nr, T, st);
+      launch_fwd_flow<8>(L, ld, ws, Bc, Yc, ldb, nr, T, st);
   }
 }
 
