@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
 
     distributed = None
     if dist is not None and not args.no_distributed:
-        n_large = args.dist_sites or {2: 120000, 4: 170000}.get(world, 200000 if world >= 8 else 100000)
+        n_large = args.dist_sites or {2: 140000, 3: 170000}.get(world, 200000 if world >= 4 else 100000)
         distributed = distributed_record(torch, dist, dev, rank, world, n_large)
 
     if rank != 0:
