@@ -460,8 +460,9 @@ def run_ours(args, rank, world, local_rank):
     # dominant kernel: the largest trailing-update launch of each factorisation (C -= P P^T on the
     # (n_pad - 2K)^2 lower triangle, K = 768 at n = 50 000), bracketed by CUDA events inside the timed region
     n_pad = (n + 127) // 128 * 128
-    # outer panel width, the rule of chol_outer() in csrc/chol.cu: 768 from 16 384 sites up, else 512
-    kk = 128 * max(1, min(int(os.environ.get("COCONS_CHOL_OUTER", "6" if n_pad >= 16384 else "4")), 16))
+    # outer panel width, the rule of chol_outer() in csrc/chol.cu: 768 from 16 384 sites up, 512 from 8192, else 256
+    kk = 128 * max(1, min(int(os.environ.get("COCONS_CHOL_OUTER",
+                                             "6" if n_pad >= 16384 else ("4" if n_pad >= 8192 else "2"))), 16))
     rest = n_pad - 2 * kk
     kernel_flops = rest * (rest + 1) / 2 * 2 * kk  # algorithmic: lower triangle incl. diagonal
     k_ms = float(np.mean(phases["kernel_ms"]))

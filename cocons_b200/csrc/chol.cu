@@ -57,13 +57,18 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
       : "d"(a), "d"(b));
 }
 
-// Tile rasterisation.  Tiles are visited band by band (16 tile rows = 2048 matrix rows per band),
-// column by column inside a band, so that the ~300 tiles in flight at any time share one 8 MB slab
-// of A rows and a few B column tiles: the operand panel (200 MB at n = 50k, larger than L2) is then
-// read from HBM about once per band instead of once per tile column.
+// Tile rasterisation.  Tiles are visited band by band (32 tile rows = 4096 matrix rows per band),
+// column by column inside a band, so that the ~300 tiles in flight at any time share one slab of A rows
+// (25 MB at K = 768, L2-resident) and a few B column tiles: the operand panel (300 MB at n = 50k, larger than
+// L2) is read from HBM once per band instead of once per tile column.  Band height 16 / 24 / 32 run at the
+// same speed (35.40 / 35.37 / 35.34 TFLOP/s, tensor-bound); the taller band re-reads the B tiles less often
+// (DRAM traffic of the largest launch 1.21x -> ~1.1x algorithmic; profiles/r02_gemm_ncu.md).
 //   ni tile rows of 128, njc tile columns of BN = 128 / W; with lower_only, tile (bi, c) exists when
 //   bi >= c / W (the matrix origin lies on the diagonal).
-constexpr int kBandRows = 16;
+#ifndef COCONS_GEMM_BAND
+#define COCONS_GEMM_BAND 32
+#endif
+constexpr int kBandRows = COCONS_GEMM_BAND;
 
 template <int W>
 __host__ __device__ __forceinline__ int64_t band_tiles(int r, int ni, int njc, int lower_only, int* full_cols_out) {
@@ -95,7 +100,7 @@ __host__ __device__ __forceinline__ int64_t total_tiles(int ni, int njc, int low
 
 // O(1) inverse of the numbering above (a CTA decodes its tile once; a linear walk over the bands
 // would cost microseconds for the far-down tiles of a 1500-band-row update).
-//   bands [0, rt): complete triangle part      count(r) = 256 W r + 136 W   (h = 16)
+//   bands [0, rt): complete triangle part      count(r) = W h^2 r + W h (h + 1) / 2   (h = kBandRows)
 //   band rt (at most one): triangle clipped by njc or by the last, shorter band - walked directly
 //   bands after it: rectangles of h x njc
 template <int W>
@@ -116,7 +121,8 @@ __host__ __device__ __forceinline__ void tile_decode(int64_t t, int ni, int njc,
   int rt = njc / (kBandRows * W);
   const int full_height = ni / kBandRows;
   if (rt > full_height) rt = full_height;
-  const int64_t per_a = 128 * W, per_b = 136 * W;  // S(r) = per_a r (r - 1) + per_b r  tiles before band r
+  // S(r) = per_a r (r - 1) + per_b r tiles before band r (h = kBandRows: W h^2 r + W h (h + 1) / 2 tiles in band r)
+  const int64_t per_a = (int64_t)W * kBandRows * kBandRows / 2, per_b = (int64_t)W * kBandRows * (kBandRows + 1) / 2;
   auto before = [&](int rr) { return per_a * rr * (int64_t)(rr - 1) + per_b * rr; };
   if (t < before(rt)) {
     const double a = (double)per_a, b = (double)(per_b - per_a);
@@ -909,7 +915,8 @@ int chol_outer(int64_t n_pad) {
     forced = e ? std::max(1, std::min(atoi(e), 16)) : 0;
   }
   if (forced > 0) return forced;
-  return n_pad >= 16384 ? 6 : 4;
+  // holes (n_pad = 5632), 8 evaluations in flight: 2 -> 300.9, 3 -> 296.4, 4 -> 288.9 evals/s; stripes (12 032): 4 best
+  return n_pad >= 16384 ? 6 : (n_pad >= 8192 ? 4 : 2);
 }
 
 int chol_factor(double* A, int64_t n_pad, int64_t ld, CholWorkspace ws, cudaStream_t st) {

@@ -1,15 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -x -q -m gpu -k "not n50k" ) > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_gpu.log
-( timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline ) > gpurun_out/r2_bench_flow.json 2> gpurun_out/r2_bench_flow.err; echo "bench rc=$?" >> gpurun_out/r2_bench_flow.err
-( timeout 600 python tools/pool_bench.py ) > gpurun_out/r2_pool.log 2>&1
-tail -3 gpurun_out/r2_pytest_gpu.log; tail -3 gpurun_out/r2_bench_flow.err
-python - <<'PY'
-import json
-for f in ("flow",):
-    try:
-        d=json.loads(open("gpurun_out/r2_bench_%s.json"%f).read().strip().splitlines()[-1])
-        print(f, d["value"], d["phases_ms"], d["repro"]["mismatches"])
-    except Exception as e: print(f, "failed", e)
-PY
-grep "evals/s" gpurun_out/r2_pool.log
+OUT=gpurun_out/r2_band.log; : > $OUT
+for h in 16 24 32; do echo "=== band $h" >> $OUT; timeout 300 tools/micro/bin/gemm_time_band$h 32768 768 50048 4 >> $OUT 2>&1; timeout 300 tools/micro/bin/gemm_time_band$h 49152 768 12032 4 >> $OUT 2>&1; done
+for o in 2 3 4 6; do echo "=== COCONS_CHOL_OUTER=$o" >> $OUT; COCONS_CHOL_OUTER=$o timeout 300 python tools/pool_bench.py 2>&1 | grep -E "in_flight=(1|8)" >> $OUT; done
+cat $OUT
