@@ -160,8 +160,11 @@ __device__ __forceinline__ void tri_decode(int64_t t, int& tr, int& tc) {
   tc = (int)(t - (int64_t)r * (r + 1) / 2);
 }
 
+#ifndef COCONS_ASM_MINBLOCKS
+#define COCONS_ASM_MINBLOCKS 8
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kAsmTile, 8) assemble_lower_kernel(int64_t n, int64_t n_out, SiteTable T,
+__global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower_kernel(int64_t n, int64_t n_out, SiteTable T,
                                                                   double global_range, double nu_fixed,
                                                                   double* __restrict__ C, int64_t ld, int col_tile0,
                                                                   int slab) {

@@ -1,8 +1,10 @@
 // Modified Bessel function K_nu(x) and the Matern correlation factor for the
 // pairwise-assembly kernel.  Replaces boost::math::cyl_bessel_k at
 // src/cocons_full.cpp:294,450,573 (reference) with a double-precision device
-// routine from the same algorithm family (Temme 1975 series, Steed/Thompson-
-// Barnett CF2, Hankel asymptotic tail), reorganised for SIMT execution:
+// routine: Temme's 1975 series for x <= 2, the trapezoidal rule on the integral
+// representation for 2 < x < 18, the Hankel asymptotic tail beyond (Steed /
+// Thompson-Barnett CF2, Boost's own middle-band method, is kept for nu > 6 and for
+// nu > 3 beyond x = 18), organised for SIMT execution:
 //   * the branch taken is decided on a warp vote, so that a warp whose lanes sit
 //     in the same band runs exactly one of the three bodies;
 //   * everything is expressed through e^x K_nu(x) so that the e^-Q factor is
@@ -149,6 +151,59 @@ COCONS_HD void bessel_k_cf2_scaled(double mu, double x, double& kmu, double& kmu
   kmu1 = kmu * (mu + x + 0.5 - h) / x;
 }
 
+// e^x K_nu(x) for the middle band 2 < x < kHankelX, 0 <= nu <= kTrapNuMax, by the trapezoidal rule on
+//     e^x K_nu(x) = int_0^inf exp(-x (cosh t - 1)) cosh(nu t) dt,
+// step h = 5/32, nodes t_k = k h.  The integrand is entire and decays double-exponentially, so the rule
+// converges geometrically: its error is ~ exp(x - pi^2 / h) (3e-20 at x = 18) and the sum is cut when a term
+// drops below 1e-17 of it - 11 terms at x = 18, 26 at x = 2, every term positive (no cancellation).  Per term:
+// one exp, cosh(k h) - 1 from a table, cosh(nu k h) from the difference form of its three-term recurrence
+// (C_{k+1} = C_k + D_{k+1}, D_{k+1} = D_k + 4 sinh^2(nu h / 2) C_k).  Worst error against 40-digit mpmath
+// on a 41 x 24 grid of (x, nu <= 6): 1.0e-15 (Steed's CF2 above: 2.9e-15) at about a third of CF2's
+// instructions - CF2 needs a division per step and ~40 steps at x = 2.
+// Generated by: mpmath, 50 digits, cosh(k * 5/32) - 1, k = 0..31.
+constexpr double kTrapH = 0.15625;
+constexpr double kTrapNuMax = 6.0;
+constexpr int kTrapNodes = 32;
+#ifdef __CUDACC__
+__constant__
+#else
+static const
+#endif
+    double kTrapC[kTrapNodes] = {
+        0.0, 0.012231886738463469997, 0.049226785060219076999, 0.11188972977761219479,
+        0.20175369297560632423, 0.32101708629361609274, 0.47259754236986293334, 0.6602032911453254225,
+        0.88842387716101573823, 1.1628424371359932486, 1.4901722845593502931, 1.878421142670688936,
+        2.3370870435875205143, 2.8773906860114650123, 3.5125499358595403409, 4.2581031851418046566,
+        5.1322894796636861166, 6.1564947149110021668, 7.3557748157527258146, 8.7594686989112350851,
+        10.4019160135750677, 12.323297218797946605, 14.570616549147269181, 17.198851915651020399,
+        20.272299872959396082, 23.866148555693112154, 28.06831706393691852, 32.981606296188367655,
+        38.726213847251883289, 45.442674494970527276, 53.295298211196782517, 62.476189803723952335};
+
+COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
+  // sinh(a), a = nu h / 2 <= 0.47: odd series to a^15 (next term 2e-18 relative)
+  const double a = 0.5 * kTrapH * nu, a2 = a * a;
+  double sh = fma(a2, 1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+  sh = fma(sh, a2, 1.0 / 39916800.0);
+  sh = fma(sh, a2, 1.0 / 362880.0);
+  sh = fma(sh, a2, 1.0 / 5040.0);
+  sh = fma(sh, a2, 1.0 / 120.0);
+  sh = fma(sh, a2, 1.0 / 6.0);
+  sh = fma(sh * a2, a, a);
+  const double delta = 4.0 * sh * sh;  // 2 (cosh(nu h) - 1)
+  double D = 0.5 * delta;              // C_1 - C_0
+  double C = 1.0 + D;                  // cosh(nu h)
+  double sum = 0.5;
+  const double nx = -x;
+  for (int k = 1; k < kTrapNodes; ++k) {
+    const double term = exp(nx * kTrapC[k]) * C;
+    sum += term;
+    if (term < 1e-17 * sum) break;
+    D = fma(delta, C, D);
+    C += D;
+  }
+  return kTrapH * sum;
+}
+
 // e^x K_nu(x) from the Hankel expansion, x >= kHankelX, 0 < nu <= kHankelNuMax; summed until the
 // terms drop below 1e-17 of the sum (14 terms at x = 25, ~36 at x = 18)
 COCONS_HD double bessel_k_hankel_scaled(double nu, double x) {
@@ -177,11 +232,15 @@ COCONS_HD double bessel_k_recur(double kmu, double kmu1, double mu, double x, in
   return kmu;
 }
 
-// which body a given (nu, x) belongs to: 0 Temme, 1 CF2, 2 Hankel
+// which body a given (nu, x) belongs to: 0 Temme, 1 CF2, 2 Hankel, 3 trapezoidal rule
 COCONS_HD int bessel_band(double nu, double x) {
   if (x <= 2.0) return 0;
-  if (x >= kHankelX && nu <= kHankelNuMax) return 2;
+  if (x >= kHankelX) return (nu <= kHankelNuMax) ? 2 : 1;
+#ifdef COCONS_BESSEL_NO_TRAP  // ablation: round 1's CF2 in the middle band
   return 1;
+#else
+  return (nu <= kTrapNuMax) ? 3 : 1;
+#endif
 }
 
 // K_nu(x) itself (unscaled) - used by tests and by callers that want the plain value
@@ -190,6 +249,7 @@ COCONS_HD double bessel_k(double nu, double x) {
   const double mu = nu - (double)nl;
   const int band = bessel_band(nu, x);
   if (band == 2) return bessel_k_hankel_scaled(nu, x) * exp(-x);
+  if (band == 3) return bessel_k_trap_scaled(nu, x) * exp(-x);
   double kmu, kmu1;
   if (band == 0) {
     const TemmeGammas G = temme_gammas(mu);
@@ -217,6 +277,8 @@ COCONS_HD double matern_corr(double nu, double Q) {
   double ks;
   if (band == 2) {
     ks = bessel_k_hankel_scaled(nu, Q);
+  } else if (band == 3) {
+    ks = bessel_k_trap_scaled(nu, Q);
   } else {
     double kmu, kmu1;
     bessel_k_cf2_scaled(mu, Q, kmu, kmu1);

@@ -222,3 +222,28 @@ def test_cocooptim_ml_follows_the_reference_penalty_layout(datasets):
         obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml, info={"lambda.Sigma": 0.1})
         with pytest.raises(NotImplementedError, match="two-step"):
             cb.cocoOptim(obj, bounds, optim_type=kind)
+
+
+def test_trapezoid_band_of_the_device_bessel_against_mpmath(tmp_path):
+    """The middle band 2 < x < 18 (most pairs of a dense model) is evaluated by the trapezoidal rule on the
+    integral representation (bessel.cuh, bessel_k_trap_scaled): dense grid against 40-digit mpmath, including
+    both band edges, nu = 0 and the nu limit at which the code switches back to CF2."""
+    src = tmp_path / "bt.cpp"
+    src.write_text('#include "bessel.cuh"\n'
+                   'extern "C" double h_t(double nu, double x){ return cocons::bessel_k_trap_scaled(nu, x); }\n'
+                   'extern "C" int h_band(double nu, double x){ return cocons::bessel_band(nu, x); }\n')
+    so = tmp_path / "libbt.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-I" + os.path.join(ROOT, "cocons_b200", "csrc"), str(src), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    lib.h_t.argtypes, lib.h_t.restype = [ctypes.c_double] * 2, ctypes.c_double
+    lib.h_band.argtypes, lib.h_band.restype = [ctypes.c_double] * 2, ctypes.c_int
+    assert lib.h_band(1.2, 2.0) == 0 and lib.h_band(1.2, 2.0000001) == 3 and lib.h_band(1.2, 17.999) == 3
+    assert lib.h_band(1.2, 18.0) == 2 and lib.h_band(6.5, 10.0) == 1 and lib.h_band(3.5, 30.0) == 1
+    mp.mp.dps = 40
+    worst = 0.0
+    for x in list(np.linspace(2.0000001, 17.9999, 33)) + [2.5, 3.0, 7.77]:
+        for nu in list(np.linspace(0.0, 6.0, 25)) + [0.5, 1.5, 2.5]:
+            ref = mp.besselk(mp.mpf(float(nu)), mp.mpf(float(x))) * mp.e ** mp.mpf(float(x))
+            worst = max(worst, float(abs((mp.mpf(lib.h_t(float(nu), float(x))) - ref) / ref)))
+    assert worst < 2.5e-15, worst

@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-OUT=gpurun_out/r2_band.log; : > $OUT
-for h in 16 24 32; do echo "=== band $h" >> $OUT; timeout 300 tools/micro/bin/gemm_time_band$h 32768 768 50048 4 >> $OUT 2>&1; timeout 300 tools/micro/bin/gemm_time_band$h 49152 768 12032 4 >> $OUT 2>&1; done
-for o in 2 3 4 6; do echo "=== COCONS_CHOL_OUTER=$o" >> $OUT; COCONS_CHOL_OUTER=$o timeout 300 python tools/pool_bench.py 2>&1 | grep -E "in_flight=(1|8)" >> $OUT; done
-cat $OUT
+OUT=gpurun_out/r2_asm_variants.log; : > $OUT
+for v in cf2_mb8 trap_mb8 trap_mb6 trap_mb5; do timeout 300 python tools/asm_time.py tools/micro/bin/lib_$v.so 30000 >> $OUT 2>&1; done
+for v in cf2_mb8 trap_mb8 trap_mb5; do timeout 300 python tools/asm_time.py tools/micro/bin/lib_$v.so 5570 >> $OUT 2>&1; done
+grep ASM_TIME $OUT
+( time timeout 900 python -m pytest tests -x -q -m gpu -k "cov or n2ll or taper" ) > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_gpu.log
