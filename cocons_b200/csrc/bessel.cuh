@@ -2,7 +2,7 @@
 // pairwise-assembly kernel.  Replaces boost::math::cyl_bessel_k at
 // src/cocons_full.cpp:294,450,573 (reference) with a double-precision device
 // routine: Temme's 1975 series for x <= 2, the trapezoidal rule on the integral
-// representation for 2 < x < 18, the Hankel asymptotic tail beyond (Steed /
+// representation for 2 < x < 25, the Hankel asymptotic tail beyond (Steed /
 // Thompson-Barnett CF2, Boost's own middle-band method, is kept for nu > 6 and for
 // nu > 3 beyond x = 18), organised for SIMT execution:
 //   * the branch taken is decided on a warp vote, so that a warp whose lanes sit
@@ -31,8 +31,9 @@ namespace cocons {
 constexpr double kPi = 3.141592653589793238462643383279502884;
 constexpr double kHalfPi = 1.570796326794896619231321691639751442;
 constexpr double kBesselEps = 1.0e-16;  // series / continued-fraction stopping level
-constexpr double kHankelX = 18.0;       // Hankel tail used for x >= kHankelX and nu <= kHankelNuMax
-constexpr double kHankelNuMax = 3.0;    // (terms shrink until k ~ 2x: ~4e-15 at x = 18, 9e-16 from x = 25 on)
+constexpr double kHankelX = 25.0;       // Hankel tail used for x >= kHankelX and nu <= kHankelNuMax
+constexpr double kHankelNuMax = 3.0;    // (terms shrink until k ~ 2x: 9e-16 from x = 25 on, ~23 terms there)
+constexpr double kTrapXHighNu = 18.0;   // for kHankelNuMax < nu <= kTrapNuMax the trapezoidal rule stops here
 constexpr int kHankelTerms = 40;
 
 // gamma1, gamma2, 1/Gamma(1+mu), 1/Gamma(1-mu) for |mu| <= 1/2
@@ -151,11 +152,12 @@ COCONS_HD void bessel_k_cf2_scaled(double mu, double x, double& kmu, double& kmu
   kmu1 = kmu * (mu + x + 0.5 - h) / x;
 }
 
-// e^x K_nu(x) for the middle band 2 < x < kHankelX, 0 <= nu <= kTrapNuMax, by the trapezoidal rule on
+// e^x K_nu(x) for the middle band (2 < x < 25 for nu <= 3, 2 < x < 18 for 3 < nu <= 6) by the trapezoidal rule on
 //     e^x K_nu(x) = int_0^inf exp(-x (cosh t - 1)) cosh(nu t) dt,
 // step h = 5/32, nodes t_k = k h.  The integrand is entire and decays double-exponentially, so the rule
-// converges geometrically: its error is ~ exp(x - pi^2 / h) (3e-20 at x = 18) and the sum is cut when a term
-// drops below 1e-17 of it - 11 terms at x = 18, 26 at x = 2, every term positive (no cancellation).  Per term:
+// converges geometrically (the error falls like exp(-pi^2 / h) against a factor growing with x and nu: measured
+// 5e-16 up to x = 25 for nu <= 3 and up to x = 21 for nu <= 6) and the sum is cut when a term drops below
+// 1e-17 of it - 13 terms at x = 25, 26 at x = 2, every term positive (no cancellation).  Per term:
 // one exp, cosh(k h) - 1 from a table, cosh(nu k h) from the difference form of its three-term recurrence
 // (C_{k+1} = C_k + D_{k+1}, D_{k+1} = D_k + 4 sinh^2(nu h / 2) C_k).  Worst error against 40-digit mpmath
 // on a 41 x 24 grid of (x, nu <= 6): 1.0e-15 (Steed's CF2 above: 2.9e-15) at about a third of CF2's
@@ -235,11 +237,11 @@ COCONS_HD double bessel_k_recur(double kmu, double kmu1, double mu, double x, in
 // which body a given (nu, x) belongs to: 0 Temme, 1 CF2, 2 Hankel, 3 trapezoidal rule
 COCONS_HD int bessel_band(double nu, double x) {
   if (x <= 2.0) return 0;
-  if (x >= kHankelX) return (nu <= kHankelNuMax) ? 2 : 1;
-#ifdef COCONS_BESSEL_NO_TRAP  // ablation: round 1's CF2 in the middle band
-  return 1;
+#ifdef COCONS_BESSEL_NO_TRAP  // ablation: round 1's layout (CF2 in the middle band, Hankel from x = 18)
+  return (x >= 18.0 && nu <= kHankelNuMax) ? 2 : 1;
 #else
-  return (nu <= kTrapNuMax) ? 3 : 1;
+  if (nu <= kHankelNuMax) return (x < kHankelX) ? 3 : 2;
+  return (nu <= kTrapNuMax && x < kTrapXHighNu) ? 3 : 1;
 #endif
 }
 

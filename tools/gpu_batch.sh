@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 OUT=gpurun_out/r2_asm_variants.log; : > $OUT
-for v in cf2_mb8 trap_mb8 trap_mb6 trap_mb5; do timeout 300 python tools/asm_time.py tools/micro/bin/lib_$v.so 30000 >> $OUT 2>&1; done
-for v in cf2_mb8 trap_mb8 trap_mb5; do timeout 300 python tools/asm_time.py tools/micro/bin/lib_$v.so 5570 >> $OUT 2>&1; done
+timeout 300 python tools/asm_time.py - 30000 >> $OUT 2>&1; timeout 300 python tools/asm_time.py - 5570 >> $OUT 2>&1; timeout 300 python tools/asm_time.py - 50000 >> $OUT 2>&1
 grep ASM_TIME $OUT
-( time timeout 900 python -m pytest tests -x -q -m gpu -k "cov or n2ll or taper" ) > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_gpu.log
+( time timeout 1200 python -m pytest tests -x -q -m gpu -s -k "not n50k" ) > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_gpu.log
+( time timeout 600 python -m pytest tests -x -q -m gpu -s -k "n50k" ) > gpurun_out/r2_pytest_n50k.log 2>&1; echo "pytest n50k rc=$?"; grep -E "n=50000|passed|failed" gpurun_out/r2_pytest_n50k.log
+grep -E "n=20000" gpurun_out/r2_pytest_gpu.log
