@@ -282,6 +282,41 @@ def golden_theta(case):
     return {k: np.array(v, dtype=np.float64) for k, v in case["theta"].items()}
 
 
+def sampled_factor_residual(ctx, locs, X, theta, m=48, seed=7):
+    """max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb) over all pairs of m sampled sites: L rows from the device
+    factor, Sigma from the oracle (the reference's compiled cov_rns on the m-site subset - an entry of cov_rns
+    depends on its two sites and theta only).  Size-independent check of assembly + factorisation."""
+    from oracle import cov
+    n = locs.shape[0]
+    rng = np.random.default_rng(seed)
+    sites = np.sort(rng.choice(n, m, replace=False))
+    rows, _ = ctx.factor_rows(sites)
+    G = rows @ rows.T
+    kind = "reference" if cov.have_reference() else "restatement"
+    S = cov.cov_rns(theta, np.asfortranarray(locs[sites]), np.asfortranarray(X[sites]), LIMITS, kind=kind)
+    d = np.sqrt(np.diag(S))
+    return float(np.max(np.abs(G - S) / np.outer(d, d))), kind, m
+
+
+def north_star_single(local_rank, n_big):
+    """north_star: one full evaluation at n = 100 000 on ONE B200 (80 GB matrix), device-timed phases, Cholesky
+    phase against the FP64 peak, and the sampled-entry residual of its factor against the reference covariance."""
+    import cocons_b200 as cb
+    from cocons_b200 import _lib
+    locs, X, z = synthetic(n_big)
+    th = theta_at(0, 0)
+    with cb.DenseLikelihood(locs, X, z, device=local_rank) as ctx:
+        t = ctx.terms(_lib.ML, th, LIMITS, th["mean"])
+        tm = ctx.timings()
+        resid, kind, m = sampled_factor_residual(ctx, locs, X, th)
+    tf = flops_chol(n_big) / (tm["factor_ms"] * 1e-3) / 1e12
+    return {"n": n_big, "eval_ms": tm["total_ms"], "assembly_ms": tm["assembly_ms"], "factor_ms": tm["factor_ms"],
+            "solve_ms": tm["solve_ms"], "chol_tflops": tf, "frac_of_derived_fp64_peak": tf / DERIVED_FP64_PEAK_TFLOPS,
+            "value": n_big * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0]),
+            "factor_residual": {"max_rel": resid, "sampled_sites": m, "entries": m * (m + 1) // 2, "sigma_from": kind,
+                                "what": "max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb), Sigma_ab from the oracle"}}
+
+
 def distributed_record(torch, dist, dev, rank, world, n_large):
     """BASELINE.json configs[3] / north_star (c): ONE matrix over all ranks (column-panel block-cyclic
     Cholesky, NCCL panel broadcast).  A golden-pinned evaluation at n = 20 000 through the same code, then
@@ -309,6 +344,21 @@ def distributed_record(torch, dist, dev, rank, world, n_large):
                 worst = max(worst, abs(v - c["neg2loglik"]) / abs(c["neg2loglik"]))
         rec["parity_n20k_rel"] = worst
         rec["parity_n20k_points"] = sorted(gold)
+    # the two drivers on the same n = 100 000 problem: rank 0 alone (look-ahead driver, one GPU), then all ranks
+    n_mid = 100000
+    single = None
+    if rank == 0:
+        single = north_star_single(dev.index, n_mid)
+    dist.barrier()
+    locs, X, z = synthetic(n_mid)
+    with DistributedDenseLikelihood(locs, X, z) as d:
+        t = d.terms(_lib.ML, theta_at(0, 0), LIMITS, THETA["mean"])
+        v_dist = n_mid * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0])
+        ph = {k: vmax(v) for k, v in d.last_phase_s.items()}
+    if rank == 0:
+        rec["agreement_n100k"] = {"single_gpu_value": single["value"], "distributed_value": v_dist,
+                                  "rel_diff": abs(single["value"] - v_dist) / abs(single["value"]),
+                                  "single_gpu": single, "distributed_eval_s": ph["assemble_factor_s"] + ph["solve_s"]}
     locs, X, z = synthetic(n_large)
     os.environ["COCONS_DIST_PROFILE"] = "1"
     with DistributedDenseLikelihood(locs, X, z) as d:
@@ -476,6 +526,7 @@ def run_ours(args, rank, world, local_rank):
     except (OSError, ValueError, KeyError):
         pass
     cpu = cpu_reference_sample(n) if world == 1 and not args.no_cpu_baseline else None
+    big = north_star_single(local_rank, 100000) if (world == 1 and not args.no_large) else None
     line = {
         "metric": "neg2loglik evals/sec (assembly+Cholesky) at n=50k", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
@@ -512,6 +563,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if big is not None:
+        line["north_star_n100k_1gpu"] = big
     if distributed is not None:
         line["distributed"] = distributed
     print(json.dumps(line))
@@ -543,6 +596,7 @@ def main():
     ap.add_argument("--no-distributed", action="store_true",
                     help="N > 1: skip the one-matrix-over-all-GPUs record (BASELINE.json configs[3])")
     ap.add_argument("--dist-sites", type=int, default=0, help="N > 1: sites of the distributed evaluation")
+    ap.add_argument("--no-large", action="store_true", help="N = 1: skip the n = 100 000 north-star evaluation")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run: device-resident arm only (no DGEMM probe, no e2e leg, no CPU sample)")
     args = ap.parse_args()

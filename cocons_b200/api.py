@@ -423,6 +423,16 @@ class DenseLikelihood:
         _lib.check(_lib.lib().cocons_ctx_get_factor(self._h, _lib.ptr(L), perm.ctypes.data_as(_lib._lp)))
         return L, perm
 
+    def factor_rows(self, sites):
+        """Rows of the kept factor for the given caller-order sites: (rows [m x n], pos [m]); the covariance of
+        sites a, b is rows[a] @ rows[b] (see cocons_ctx_factor_rows)."""
+        sites = np.ascontiguousarray(np.asarray(sites, dtype=np.int64))
+        rows = np.empty((len(sites), self.n))
+        pos = np.empty(len(sites), dtype=np.int64)
+        _lib.check(_lib.lib().cocons_ctx_factor_rows(self._h, sites.ctypes.data_as(_lib._lp), len(sites),
+                                                     _lib.ptr(rows), pos.ctypes.data_as(_lib._lp)))
+        return rows, pos
+
     def timings(self):
         ms = np.empty(4)
         _lib.lib().cocons_ctx_timings(self._h, _lib.ptr(ms))

@@ -1234,6 +1234,35 @@ int cocons_ctx_get_factor(cocons_ctx* c, double* L, int64_t* perm) {
   return 0;
 }
 
+int cocons_ctx_factor_rows(cocons_ctx* c, const int64_t* sites, int64_t m, double* rows, int64_t* pos) {
+  if (!c || !sites || !rows || !pos || m <= 0) {
+    set_error("factor_rows: bad argument");
+    return COCONS_ERR_ARG;
+  }
+  if (!c->factor_valid) {
+    set_error("factor_rows: no factor kept");
+    return COCONS_ERR_STATE;
+  }
+  cudaSetDevice(c->device);
+  const int64_t np = c->n_pad, n = c->n;
+  std::vector<int64_t> inv((size_t)n);
+  for (int64_t s = 0; s < n; ++s) inv[(size_t)c->perm[(size_t)s]] = s;
+  for (int64_t a = 0; a < m; ++a) {
+    if (sites[a] < 0 || sites[a] >= n) {
+      set_error("factor_rows: site %lld out of range", (long long)sites[a]);
+      return COCONS_ERR_ARG;
+    }
+    const int64_t i = inv[(size_t)sites[a]];
+    pos[a] = i;
+    double* out = rows + (size_t)a * n;
+    // row i of the column-major factor: one element per column, columns 0..i
+    COCONS_CUDA_TRY(cudaMemcpy2D(out, sizeof(double), c->dA + i, sizeof(double) * np, sizeof(double), (size_t)(i + 1),
+                                 cudaMemcpyDeviceToHost));
+    for (int64_t k = i + 1; k < n; ++k) out[k] = 0.0;
+  }
+  return 0;
+}
+
 int cocons_ctx_timings(cocons_ctx* c, double* ms4) {
   if (!c || !ms4) return COCONS_ERR_ARG;
   for (int i = 0; i < 4; ++i) ms4[i] = c->ms[i];

@@ -189,6 +189,12 @@ int cocons_sim_cond(cocons_ctx* ctx, int64_t m, const double* locs_pred, const d
  * (perm[i] = original index of re-ordered site i).  For tests. */
 int cocons_ctx_get_factor(cocons_ctx* ctx, double* L, int64_t* perm);
 
+/* Rows of the kept factor for m caller-order sites: rows[a*n + k] = L[pos[a], k] (zero for k > pos[a]),
+ * pos[a] = position of sites[a] in the re-ordered matrix.  (L L^T)[pos[a], pos[b]] is then the covariance of
+ * sites a and b (base::chol, R/neg2loglikelihood.R:200): the residual check of the factorisation at sizes
+ * whose full factor does not fit a host (n = 100 000: 80 GB). */
+int cocons_ctx_factor_rows(cocons_ctx* ctx, const int64_t* sites, int64_t m, double* rows, int64_t* pos);
+
 /* per-phase device times of the last evaluation, milliseconds (CUDA events on
  * the context's stream): [0] site+assembly [1] factorisation [2] solves+reductions [3] total */
 int cocons_ctx_timings(cocons_ctx* ctx, double* ms4);

@@ -116,3 +116,16 @@ def test_n50k_against_reference_golden_and_bit_reproducible():
             assert rel < 1e-8 and rl < 1e-8 and rq < 1e-8
         for name, c in sorted(gold.items()):
             assert _terms(ctx, _theta(c)) == seen[name], name
+
+
+def test_sampled_entries_of_the_factor_reproduce_the_reference_covariance():
+    """(L L^T)_ab for sampled sites against the reference's cov_rns on the same sites: a size-independent residual
+    check of assembly + factorisation (bench.py reports it at n = 100 000, where no CPU oracle can factor)."""
+    n = 20000
+    locs, X, z = bench.synthetic(n)
+    th = bench.theta_at(0, 0)
+    with cb.DenseLikelihood(locs, X, z) as ctx:
+        ctx.terms(_lib.ML, th, bench.LIMITS, th["mean"])
+        resid, kind, m = bench.sampled_factor_residual(ctx, locs, X, th, m=64)
+    print("sampled factor residual at n=%d over %d sites (%s covariance): %.2e" % (n, m, kind, resid))
+    assert resid < 1e-11
