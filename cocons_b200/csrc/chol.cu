@@ -355,15 +355,22 @@ __global__ void __launch_bounds__(GemmCfg<BN, NU>::kThreads, GemmCfg<BN, NU>::kM
         hi.x = acc[a][2 * u][1];
         hi.y = acc[a][2 * u + 1][1];
       } else {
-        lo = __ldcv(p);  // C was written by an earlier kernel, possibly through another SM: never from a stale L1 line
-        hi = __ldcv(p + 1);
+        // C is touched once per launch: streaming loads and stores (evict-first), so that the 19 GB of C going
+        // through L2 do not push out the A slab and the B tiles that the other CTAs of the band re-use
+        lo = __ldcs(p);
+        hi = __ldcs(p + 1);
         lo.x -= acc[a][2 * u][0];
         lo.y -= acc[a][2 * u + 1][0];
         hi.x -= acc[a][2 * u][1];
         hi.y -= acc[a][2 * u + 1][1];
       }
-      p[0] = lo;
-      p[1] = hi;
+      if (ASSIGN) {
+        p[0] = lo;
+        p[1] = hi;
+      } else {
+        __stcs(p, lo);
+        __stcs(p + 1, hi);
+      }
     }
   }
 }
