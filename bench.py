@@ -298,19 +298,55 @@ def sampled_factor_residual(ctx, locs, X, theta, m=48, seed=7):
     return float(np.max(np.abs(G - S) / np.outer(d, d))), kind, m
 
 
-def north_star_single(local_rank, n_big):
+def north_star_single(local_rank, n_big, with_predict=False):
     """north_star: one full evaluation at n = 100 000 on ONE B200 (80 GB matrix), device-timed phases, Cholesky
     phase against the FP64 peak, and the sampled-entry residual of its factor against the reference covariance."""
     import cocons_b200 as cb
     from cocons_b200 import _lib
-    locs, X, z = synthetic(n_big)
+    m_pred = n_big // 5 if with_predict else 0
+    locs_all, X_all, z_all = synthetic(n_big + m_pred)  # one stream: the first n_big sites train, the rest predict
+    locs, X, z = np.asfortranarray(locs_all[:n_big]), np.asfortranarray(X_all[:n_big]), z_all[:n_big]
     th = theta_at(0, 0)
+    cfg4 = None
     with cb.DenseLikelihood(locs, X, z, device=local_rank) as ctx:
         t = ctx.terms(_lib.ML, th, LIMITS, th["mean"])
         tm = ctx.timings()
         resid, kind, m = sampled_factor_residual(ctx, locs, X, th)
+        if with_predict:
+            # BASELINE.json configs[4]: cocoPredict (type "pred") for n/5 new sites and one cocoSim draw on the KEPT
+            # factor (R/predict.R:136-183, R/sim.R:87-121), with size-independent checks
+            import torch
+            lp, Xp = np.asfortranarray(locs_all[n_big:]), np.asfortranarray(X_all[n_big:])
+            r = z - X @ th["mean"]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sto, expl = ctx.predict(lp, Xp, r)
+            t_pred = time.perf_counter() - t0
+            prior = np.exp(Xp @ th["std.dev"]) + np.exp(Xp @ th["nugget"])
+            rng = np.random.default_rng(SEED + 1)
+            sub = np.sort(rng.choice(m_pred, 300, replace=False))
+            s2, e2 = ctx.predict(lp[sub], Xp[sub], r)
+            # kriging at TRAINING coordinates interpolates: a coincident pair takes variance + nugget
+            # (src/cocons_full.cpp:284-286), so the predictor returns the residual itself and explains everything
+            tr = np.sort(rng.choice(n_big, 64, replace=False))
+            s3, e3 = ctx.predict(locs[tr], X[tr], r)
+            prior_tr = np.exp(X[tr] @ th["std.dev"]) + np.exp(X[tr] @ th["nugget"])
+            eps = rng.standard_normal((n_big, 1))
+            t0 = time.perf_counter()
+            draw = ctx.sim(eps)
+            t_sim = time.perf_counter() - t0
+            cfg4 = {"prediction_sites": m_pred, "predict_s": t_pred, "sim_s": t_sim,
+                    "predict_tflops": 2.0 * m_pred * n_big * n_big / 2 / t_pred / 1e12,
+                    "checks": {"finite": bool(np.all(np.isfinite(sto)) and np.all(np.isfinite(expl))),
+                               "explained_within_prior": bool(np.all(expl >= 0) and np.all(expl <= prior * (1 + 1e-9))),
+                               "subset_of_300_bit_identical": bool(np.array_equal(s2, sto[sub]) and np.array_equal(e2, expl[sub])),
+                               "interpolation_at_64_training_sites_rel": float(np.max(np.abs(s3 - r[tr]) / np.abs(r[tr]))),
+                               "explained_equals_prior_at_training_sites_rel": float(np.max(np.abs(e3 - prior_tr) / prior_tr)),
+                               "draw_variance_over_model_variance": float(np.mean(
+                                   draw[:, 0] ** 2 / (np.exp(X @ th["std.dev"]) + np.exp(X @ th["nugget"]))))}}
     tf = flops_chol(n_big) / (tm["factor_ms"] * 1e-3) / 1e12
-    return {"n": n_big, "eval_ms": tm["total_ms"], "assembly_ms": tm["assembly_ms"], "factor_ms": tm["factor_ms"],
+    return {"n": n_big, "config4_predict_sim": cfg4,
+            "eval_ms": tm["total_ms"], "assembly_ms": tm["assembly_ms"], "factor_ms": tm["factor_ms"],
             "solve_ms": tm["solve_ms"], "chol_tflops": tf, "frac_of_derived_fp64_peak": tf / DERIVED_FP64_PEAK_TFLOPS,
             "value": n_big * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0]),
             "factor_residual": {"max_rel": resid, "sampled_sites": m, "entries": m * (m + 1) // 2, "sigma_from": kind,
@@ -526,7 +562,7 @@ def run_ours(args, rank, world, local_rank):
     except (OSError, ValueError, KeyError):
         pass
     cpu = cpu_reference_sample(n) if world == 1 and not args.no_cpu_baseline else None
-    big = north_star_single(local_rank, 100000) if (world == 1 and not args.no_large) else None
+    big = north_star_single(local_rank, 100000, with_predict=True) if (world == 1 and not args.no_large) else None
     line = {
         "metric": "neg2loglik evals/sec (assembly+Cholesky) at n=50k", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
