@@ -380,6 +380,25 @@ def distributed_record(torch, dist, dev, rank, world, n_large):
                 worst = max(worst, abs(v - c["neg2loglik"]) / abs(c["neg2loglik"]))
         rec["parity_n20k_rel"] = worst
         rec["parity_n20k_points"] = sorted(gold)
+    # the optimiser's fan-out (SURVEY §8f N1, R/optim.R:237-259): 2p + 1 = 61 finite-difference points of the n = 20 000
+    # problem dealt over the ranks by distributed.fan_out (NCCL all_gather of the values), against rank 0's own values
+    from cocons_b200.distributed import fan_out
+    locs, X, z = synthetic(20000)
+    pts = [theta_at(k, 0) for k in range(61)]
+    with cb.DenseLikelihood(locs, X, z, device=dev.index) as ctx:
+        def f(th):
+            t = ctx.terms(_lib.ML, th, LIMITS, th["mean"])
+            return 20000 * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0])
+        f(pts[0])
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vals = fan_out(pts, f)
+        t_fan = vmax(time.perf_counter() - t0)
+        local = [f(th) for th in pts[:8]] if rank == 0 else None
+    if rank == 0:
+        rec["fan_out"] = {"points": len(pts), "n": 20000, "seconds": t_fan, "evals_per_s": len(pts) / t_fan,
+                          "bit_identical_to_rank0_on_first_8": bool(vals[:8] == local)}
     # the two drivers on the same n = 100 000 problem: rank 0 alone (look-ahead driver, one GPU), then all ranks
     n_mid = 100000
     single = None

@@ -29,6 +29,7 @@ from .api import (  # noqa: F401
     getCovMatrix,
     getDensityFromDelta,
     getDesignMatrix,
+    getEstims,
     getHessian,
     getModelLists,
     getScale,

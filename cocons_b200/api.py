@@ -13,6 +13,8 @@ Reference lines are cited per function.  R lists become dicts, formulas become
 strings such as "~ 1 + cov_x + cov_y", data.frames become dicts of columns (or
 pandas DataFrames).
 """
+import copy
+
 import numpy as np
 
 from . import _lib
@@ -674,8 +676,99 @@ def fd_value_and_grad(fn, theta, lower, upper, ndeps, forward=False, group=None,
     return f0, grad
 
 
+def getEstims(coco_object):
+    """R/getFunctions.R:357-363."""
+    par_pos = getDesignMatrix(coco_object.model_list, coco_object.data)["par.pos"]
+    return getModelLists(coco_object.output["par"], par_pos, "diff")
+
+
+def _update_coco_first_step(coco_object, output, boundaries):
+    """.cocons.update.coco.first.step, R/checkFunctions.R:515-603: after the penalised first fit, coefficients
+    with |estimate| <= sparse.point leave their aspect's formula (an aspect left with at most one coefficient
+    becomes "~1"; a lone intercept is never dropped) and the matching entries leave the boundaries.  Mirrored
+    statement by statement, including the way the boundaries are pruned independently of the formulas."""
+    par_pos = getDesignMatrix(coco_object.model_list, coco_object.data)["par.pos"]
+    free = {k: isinstance(v, np.ndarray) and v.dtype == bool for k, v in par_pos.items()}
+    nparams = {k: int(par_pos[k].sum()) if free[k] else 0 for k in par_pos}
+    fitted = copy.copy(coco_object)
+    fitted.info = dict(coco_object.info)
+    fitted.output = dict(output)
+    parss = getEstims(fitted)
+    cut = fitted.info["sparse.point"]
+    new_formulas = dict(coco_object.model_list)
+    columns = ["(Intercept)"] + _union_labels(coco_object.model_list)
+
+    def small(name):  # 1-based positions among the aspect's own coefficients, as R's which()
+        est = parss[name][par_pos[name]]
+        return [i + 1 for i, v in enumerate(est) if abs(v) <= cut]
+
+    for name in DICTIONARY:
+        if not is_formula(coco_object.model_list[name]):
+            continue
+        to_zero = small(name)
+        if not to_zero:
+            continue
+        if len(to_zero) in (nparams[name] - 1, nparams[name]):
+            new_formulas[name] = "~1"
+            continue
+        if to_zero == [1]:
+            continue
+        # drop.terms(terms(formula), dropx = to_zero - 1): term k of the formula is the aspect's coefficient k + 1
+        own = [columns[j] for j in np.flatnonzero(par_pos[name])]
+        intercept, labels = _terms(coco_object.model_list[name])
+        drop = {own[k - 1] for k in to_zero if k - 1 >= (1 if intercept else 0)}
+        keep = [l for l in labels if l not in drop]
+        new_formulas[name] = "~" + " + ".join((["1"] if intercept and keep else []) + keep) if keep else "~1"
+    npar = len(output["par"])
+    gone = np.zeros(npar, dtype=bool)
+    where = 0
+    for name in DICTIONARY:
+        if not is_formula(coco_object.model_list[name]):
+            continue
+        to_zero = small(name)
+        if 1 in to_zero and len(to_zero) > 1:
+            to_zero = to_zero[1:]
+        if to_zero == [1]:
+            where += nparams[name]
+            continue
+        for k in to_zero:
+            gone[where + k - 1] = True
+        where += nparams[name]
+    pruned = {k: np.asarray(v, dtype=np.float64)[~gone] for k, v in boundaries.items()}
+    out = copy.copy(coco_object)
+    out.info = dict(coco_object.info, boundaries=pruned)
+    out.model_list = new_formulas
+    out.output = dict(output)
+    return out
+
+
+def _union_labels(model_list):
+    labels = []
+    for v in model_list.values():
+        if is_formula(v):
+            for l in _terms(v)[1]:
+                if l not in labels:
+                    labels.append(l)
+    return labels
+
+
+def _cocoOptim_two_step(coco_object, boundaries, ncores, safe, optim_control, device, forward):
+    """R/optim.R:127-230: penalised first fit (lambda.Sigma, lambda.betas, lambda.reg), model pruning at
+    sparse.point, second fit of the pruned model with lambda = (0, 0, lambda.reg) from the pruned boundaries."""
+    obj = copy.copy(coco_object)
+    obj.info = dict(coco_object.info)
+    if obj.info.get("sparse.point") is None:
+        obj.info["sparse.point"] = 1e-4  # getOption("cocons.sparse.point"), R/cocons.R:32
+    first = cocoOptim(copy.copy(obj), boundaries, ncores, safe, "ml", optim_control, device, forward, _first_step=True)
+    pen = _update_coco_first_step(obj, first.output, boundaries)
+    b2 = pen.info["boundaries"]
+    second = cocoOptim(pen, b2, ncores, safe, "ml", optim_control, device, forward, _first_step=False)
+    second.info["first.step"] = {"par": first.output["par"], "value": first.output["value"]}
+    return second
+
+
 def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml", optim_control=None, device=0,
-              forward=False):
+              forward=False, _first_step=None):
     """R/optim.R:65-365 (dense) and :366-690 (sparse, see _cocoOptim_sparse).  L-BFGS-B (scipy) stands in for optimParallel's optimiser; its
     gradient is the same batched finite-difference scheme (fd_value_and_grad), whose independent
     objective evaluations run on the device-resident context of each rank - across all GPUs when
@@ -690,15 +783,14 @@ def cocoOptim(coco_object, boundaries, ncores="auto", safe=True, optim_type="ml"
     lim = coco_object.info["smooth.limits"]
     optim_type = optim_type.lower()  # R/optim.R:113
     # every dense branch optimises with lambda = c(0, 0, lambda.reg) (R/optim.R:248, 287, 316) except the first
-    # step of the penalised two-step "ml" fit (:127-223: lambda.Sigma / lambda.betas > 0, then the model is pruned
-    # at sparse.point by .cocons.update.coco.first.step and refitted) - that caller-side model surgery is not
-    # mirrored: refuse rather than return a different optimum
+    # step of the penalised two-step "ml" fit (:127-223): lambda.Sigma / lambda.betas > 0, then the model is pruned
+    # at sparse.point and refitted without those two penalties
     lam = (0.0, 0.0, coco_object.info["lambda.reg"])
-    if optim_type == "ml" and coco_object.type == "dense" and (
+    if _first_step is None and optim_type == "ml" and coco_object.type == "dense" and (
             coco_object.info.get("lambda.Sigma", 0) > 0 or coco_object.info.get("lambda.betas", 0) > 0):
-        raise NotImplementedError("cocoOptim(optim_type='ml') with lambda.Sigma / lambda.betas > 0 is the reference's "
-                                  "penalised two-step fit (R/optim.R:127-223), which is not mirrored; the penalised "
-                                  "objective itself is available through GetNeg2loglikelihood(lambda=...)")
+        return _cocoOptim_two_step(coco_object, boundaries, ncores, safe, optim_control, device, forward)
+    if _first_step:
+        lam = (coco_object.info["lambda.Sigma"], coco_object.info["lambda.betas"], coco_object.info["lambda.reg"])
     ctrl = {"maxiter": 500, "ftol": 1e-8, "maxcor": 100}  # R/profile.R:9-16 (factr, maxit, lmm)
     ctrl.update(optim_control or {})
     ndeps = ctrl.pop("ndeps", np.finfo(float).eps ** 0.25)

@@ -168,3 +168,28 @@ def test_hessian_mirrors_the_reference_scheme(datasets):
     assert np.array_equal(Hg, Hg.T)
     # both are differences of O(1e2) values divided by eps^2 = 1.5e-8: agreement to ~1e-5 of |f|/eps^2 scale
     assert np.max(np.abs(Hg - Hr)) < 1e-3 * max(1.0, np.max(np.abs(Hr)))
+
+
+def test_penalised_two_step_fit_prunes_and_refits(datasets):
+    """R/optim.R:127-230: with lambda.Sigma / lambda.betas > 0 the 'ml' fit is penalised, small coefficients are
+    pruned at sparse.point and the pruned model is refitted with lambda = (0, 0, lambda.reg).  A covariate that
+    is pure noise for the standard deviation must leave the model under a strong penalty, and the second fit
+    must be a plain ML fit of the model that is left."""
+    H = datasets["holes_training"][:120]
+    rng = np.random.default_rng(5)
+    noise = rng.standard_normal(120)
+    data = {"x": H[:, 0], "y": H[:, 1], "cov_x": H[:, 2], "noise": noise}
+    ml = {"mean": 0, "std.dev": "~ 1 + noise", "scale": "~ 1", "aniso": 0, "tilt": 0, "smooth": 1.5, "nugget": -np.inf}
+    obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml, info={"lambda.Sigma": 5.0, "sparse.point": 1e-3})
+    bounds = {"theta_init": np.array([0.0, 0.0, -1.0]), "theta_lower": np.array([-4.0, -2.0, -6.0]),
+              "theta_upper": np.array([4.0, 2.0, 4.0])}
+    fit = cb.cocoOptim(obj, bounds, optim_control={"maxiter": 60})
+    assert fit.model_list["std.dev"].replace(" ", "") == "~1", fit.model_list
+    assert len(fit.output["par"]) == 2 and len(fit.info["boundaries"]["theta_init"]) == 2
+    assert abs(fit.info["first.step"]["par"][1]) <= 1e-3
+    # the refit is the unpenalised objective of the pruned model at its optimum
+    dm = cb.getDesignMatrix(fit.model_list, fit.data)
+    X = cb.getScale(dm["model.matrix"])["std.covs"]
+    v = cb.GetNeg2loglikelihood(fit.output["par"], dm["par.pos"], fit.locs, X, fit.info["smooth.limits"], fit.z,
+                                120, (0.0, 0.0, 0.0))
+    assert abs(v - fit.output["value"]) <= 1e-9 * abs(v)

@@ -210,18 +210,30 @@ def test_taper_entry_points_validate_the_pattern_before_touching_a_device():
                 info={"taper": cb.cov_wend1, "delta": 0.1})
 
 
-def test_cocooptim_ml_follows_the_reference_penalty_layout(datasets):
-    """R/optim.R:113 lower-cases optim.type before anything else; :127 sends lambda.Sigma / lambda.betas > 0
-    with 'ml' into the penalised two-step fit, which is not mirrored: refused before any device call,
-    whatever the case of the type string."""
+def test_two_step_model_pruning_mirrors_the_reference(datasets):
+    """.cocons.update.coco.first.step (R/checkFunctions.R:515-603) on a fabricated first-step output: small
+    coefficients leave their formula and the boundaries; an aspect left with <= 1 coefficient becomes "~1"; a
+    lone small intercept stays.  Host logic only - no device call."""
+    from cocons_b200.api import _update_coco_first_step
     H = datasets["holes_training"][:40]
     data = {"x": H[:, 0], "y": H[:, 1], "cov_x": H[:, 2], "cov_y": H[:, 3]}
-    ml = {"mean": 0, "std.dev": "~ 1 + cov_x", "scale": "~ 1", "aniso": 0, "tilt": 0, "smooth": 1.5, "nugget": -np.inf}
-    bounds = {"theta_init": np.zeros(3), "theta_lower": -3 * np.ones(3), "theta_upper": 3 * np.ones(3)}
-    for kind in ("ml", "ML"):
-        obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml, info={"lambda.Sigma": 0.1})
-        with pytest.raises(NotImplementedError, match="two-step"):
-            cb.cocoOptim(obj, bounds, optim_type=kind)
+    ml = {"mean": "~ 1 + cov_x", "std.dev": "~ 1 + cov_x + cov_y", "scale": "~ 1 + cov_x + cov_y", "aniso": 0,
+          "tilt": 0, "smooth": 1.5, "nugget": "~ 1"}
+    obj = cb.coco("dense", data, H[:, :2], H[:, 4], ml, info={"lambda.Sigma": 0.1, "sparse.point": 1e-4})
+    #        mean (2)      std.dev (3)        scale (3)          nugget (1)
+    par = np.array([0.3, 2e-5, 0.5, 1e-6, 0.2, 1e-7, 3e-5, 4e-5, 5e-5])
+    bounds = {"theta_init": np.arange(9.0), "theta_lower": np.arange(9.0) - 10, "theta_upper": np.arange(9.0) + 10}
+    pen = _update_coco_first_step(obj, {"par": par}, bounds)
+    # getEstims works on the 'diff' image: std.dev = (a + b) / 2, scale = (a - b) / 2 for shared columns
+    est = cb.getModelLists(par, cb.getDesignMatrix(ml, data)["par.pos"], "diff")
+    assert abs(est["std.dev"][1]) <= 1e-4 and abs(est["scale"][1]) <= 1e-4  # cov_x is small in both
+    assert pen.model_list["mean"] == "~1"            # 1 of 2 small -> n - 1 -> "~1"
+    assert pen.model_list["std.dev"] == "~1 + cov_y"  # only cov_x small
+    assert pen.model_list["nugget"].replace(" ", "") == "~1"  # a lone small intercept stays an intercept
+    assert pen.model_list["aniso"] == 0 and pen.model_list["smooth"] == 1.5
+    kept = pen.info["boundaries"]["theta_init"]
+    assert 1.0 not in kept and 3.0 not in kept and 0.0 in kept and 8.0 in kept
+    assert all(len(v) == len(kept) for v in pen.info["boundaries"].values())
 
 
 def test_trapezoid_band_of_the_device_bessel_against_mpmath(tmp_path):
