@@ -36,47 +36,48 @@ constexpr double kHankelNuMax = 3.0;    // (terms shrink until k ~ 2x: 9e-16 fro
 constexpr double kTrapXHighNu = 18.0;   // for kHankelNuMax < nu <= kTrapNuMax the trapezoidal rule stops here
 constexpr int kHankelTerms = 40;
 
-// exp(y) for -708 <= y < 709 (below: 0), the exponential of the hot loops.  Same algorithm as every libm
-// (n = round(y / ln 2), two-piece reduction r = y - n ln 2, |r| <= 0.347, e^r = 1 + r + r^2 q(r) with the
-// Taylor coefficients to r^13: truncation 4e-18, 2^n added to the exponent field), but with the coefficients
-// in constant memory, so that on the device every Horner step is ONE DFMA with a constant-bank operand: the
-// library exp materialises each 64-bit literal with two UMOVs (ncu's source view of round 1's assembly kernel:
-// 10 % of all executed instructions were UMOV).  ~19 instructions against ~28; the trapezoidal rule below
-// calls it once per node.  Worst error against 40-digit mpmath on 2e5 arguments: < 1 ulp (tests/test_host.py).
+// exp(y) for -708 <= y < 709 (below: 0), the exponential of the hot loops (one call per node of the
+// trapezoidal rule below: ~17 per pair of the assembly kernel).  Table-driven: N = round(32 y / ln 2) = 32 n + j,
+// r = y - N ln2/32 (two-piece, |r| <= 0.0109), e^y = 2^n 2^(j/32) e^r with 2^(j/32) from a 32-entry table and
+// e^r = 1 + r + r^2 (1/2 + r/6 + r^2/24 + r^3/120 + r^4/720) (truncation 3e-18): 11 FP64 instructions, the
+// library routine (and a first version here with a degree-13 polynomial and no table) needs 19 plus two UMOVs
+// per 64-bit literal - ncu's source view of the assembly kernel: 11 % UMOV, 7 % LDCU.  The table is read with
+// ld.global.nc (256 B, two lines: lanes with different j do not serialise as they would on the constant
+// cache).  Worst error against long double on 25 000 arguments: 1.5 ulp (tests/test_host.py).
 #ifdef __CUDACC__
-__constant__
-#else
-static const
+__device__
 #endif
-    double kExpC[12] = {0.5,
-                        0.16666666666666666667,
-                        0.041666666666666666667,
-                        0.0083333333333333333333,
-                        0.0013888888888888888889,
-                        0.0001984126984126984127,
-                        0.000024801587301587301587,
-                        2.7557319223985890653e-6,
-                        2.7557319223985890653e-7,
-                        2.5052108385441718775e-8,
-                        2.0876756987868098979e-9,
-                        1.6059043836821614599e-10};
+    static const double kExp2Tab[32] = {
+        1.0, 1.0218971486541166782, 1.0442737824274138403, 1.0671404006768236182,
+        1.0905077326652576592, 1.1143867425958925363, 1.1387886347566916537, 1.1637248587775775138,
+        1.1892071150027210667, 1.2152473599804688781, 1.2418578120734840486, 1.2690509571917332226,
+        1.2968395546510096659, 1.3252366431597412946, 1.3542555469368927283, 1.3839098819638319549,
+        1.4142135623730950488, 1.44518080697704662, 1.4768261459394993114, 1.5091644275934227398,
+        1.5422108254079408236, 1.5759808451078864865, 1.6104903319492543082, 1.6457554781539648445,
+        1.6817928305074290861, 1.7186192981224779156, 1.7562521603732994831, 1.7947090750031071864,
+        1.8340080864093424635, 1.8741676341102999013, 1.9152065613971472939, 1.957144124175400269};
 
 COCONS_HD double exp_poly(double y) {
   if (y < -708.0) return 0.0;
-  const double kMagic = 6755399441055744.0;  // 2^52 + 2^51: the low word of y log2(e) + kMagic is round(y / ln 2)
-  const double t = fma(y, 1.4426950408889634074, kMagic);
+  const double kMagic = 6755399441055744.0;  // 2^52 + 2^51: the low word of 32 y log2(e) + kMagic is N
+  const double t = fma(y, 46.166241308446829036, kMagic);
   const double fn = t - kMagic;
-  double r = fma(fn, -6.93147180369123816490e-01, y);
-  r = fma(fn, -1.90821492927058770002e-10, r);
-  double q = kExpC[11];
-#pragma unroll
-  for (int k = 10; k >= 0; --k) q = fma(q, r, kExpC[k]);
-  const double e = fma(q * r, r, r) + 1.0;  // in [0.70, 1.42]
+  double r = fma(fn, -0.02166084938653512, y);  // ln2/32, upper 32 bits: fn * hi is exact
+  r = fma(fn, -5.9631716539705866e-12, r);
+  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  const double p = fma(q * r, r, r);  // e^r - 1
 #ifdef __CUDA_ARCH__
-  const int n = __double2loint(t);
-  return __hiloint2double(__double2hiint(e) + (n << 20), __double2loint(e));
+  const int N = __double2loint(t);
+  const double T = __ldg(&kExp2Tab[N & 31]);
+  const double e = fma(T, p, T);
+  return __hiloint2double(__double2hiint(e) + ((N >> 5) << 20), __double2loint(e));
 #else
-  return ldexp(e, (int)fn);
+  const long long N = (long long)fn;
+  const double T = kExp2Tab[N & 31];
+  return ldexp(fma(T, p, T), (int)(N >> 5));
 #endif
 }
 
@@ -242,7 +243,11 @@ COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
   const double nx = -x;
   // fully unrolled (the node constants become constant-bank operands), exit test after every second node;
   // the 31st node is never needed (26 nodes at x = 2, the lower end of the band)
+#ifdef COCONS_TRAP_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int k = 1; k < kTrapNodes - 1; k += 2) {
     const double t1 = exp_poly(nx * kTrapC[k]) * C;
     D = fma(delta, C, D);

@@ -252,11 +252,11 @@ def test_trapezoid_band_of_the_device_bessel_against_mpmath(tmp_path):
     lib.h_t.argtypes, lib.h_t.restype = [ctypes.c_double] * 2, ctypes.c_double
     lib.h_band.argtypes, lib.h_band.restype = [ctypes.c_double] * 2, ctypes.c_int
     lib.h_e.argtypes, lib.h_e.restype = [ctypes.c_double], ctypes.c_double
-    # the constant-bank exponential of the hot loops: within an ulp of the true value over its whole range
+    # the table-driven exponential of the hot loops: within 1.5 ulp of the true value over its whole range
     ys = np.concatenate([-np.exp(np.random.default_rng(3).uniform(np.log(1e-9), np.log(708), 20000)),
                          np.random.default_rng(4).uniform(-50, 40, 5000), [0.0, -0.3465, 0.3466, -707.9, 700.0]])
     worst_e = max(abs(lib.h_e(float(y)) / np.exp(np.longdouble(float(y))) - 1) for y in ys)
-    assert worst_e < 2.3e-16, worst_e
+    assert worst_e < 3.4e-16, worst_e  # 1.5 ulp
     assert lib.h_e(-709.0) == 0.0
     assert lib.h_band(1.2, 2.0) == 0 and lib.h_band(1.2, 2.0000001) == 3 and lib.h_band(3.0, 24.999) == 3
     assert lib.h_band(1.2, 25.0) == 2 and lib.h_band(6.5, 10.0) == 1 and lib.h_band(3.5, 30.0) == 1
