@@ -298,6 +298,49 @@ def sampled_factor_residual(ctx, locs, X, theta, m=48, seed=7):
     return float(np.max(np.abs(G - S) / np.outer(d, d))), kind, m
 
 
+def reference_datasets_record(local_rank):
+    """BASELINE.json configs[0] / [1]: the reference's own data sets (holes n = 5570, stripes n = 11 977, shipped as
+    tests/golden/datasets.npz) - the all-aspects ML objective against the committed golden (reference-compiled
+    covariance + LAPACK), evaluations/s one at a time and with 8 in flight on this GPU (the optimiser's
+    finite-difference points, R/optim.R:237-259)."""
+    import cocons_b200 as cb
+    from cocons_b200 import _lib
+    D = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))
+    with open(os.path.join(ROOT, "tests", "golden", "n2ll_cases.json")) as f:
+        gold = {c["name"]: c for c in json.load(f)["cases"]}
+    out = {}
+    for name, key, cols in (("holes", "holes_training", [2, 3]), ("stripes", "stripes_training", [2, 3, 4])):
+        c = gold[name + "_full_general"]
+        M, n = D[key], c["n"]
+        X = cb.getScale(np.column_stack([np.ones(n)] + [M[:n, k] for k in cols]))["std.covs"]
+        pp = {k: (np.array(v, dtype=bool) if isinstance(v, list) else v) for k, v in c["par_pos"].items()}
+        v = cb.GetNeg2loglikelihood(np.array(c["theta"]), pp, M[:n, :2], X, c["limits"], M[:n, -1], n, c["lambda"])
+        tl = cb.getModelLists(np.array(c["theta"]), pp, "diff")
+        pts = []
+        for k in range(32):
+            t = {a: x.copy() for a, x in tl.items()}
+            t["scale"][0] += 1e-4 * k
+            pts.append(t)
+
+        def f(ctx, t):
+            return ctx.terms(_lib.ML, t, c["limits"], t["mean"])["logdet"]
+        rates, ref = {}, None
+        for size in (1, 8):
+            with cb.DenseLikelihoodPool(M[:n, :2], X, M[:n, -1], size=size, device=local_rank) as pool:
+                pool.map(f, pts[:size])
+                t0 = time.perf_counter()
+                vals = pool.map(f, pts)
+                rates[size] = len(pts) / (time.perf_counter() - t0)
+            if ref is None:
+                ref = vals
+            same = bool(vals == ref)
+        out[name] = {"n": n, "p": X.shape[1], "neg2loglik_rel_err_vs_golden": abs(v - c["values"]["ml"]) / abs(c["values"]["ml"]),
+                     "evals_per_s_one_at_a_time": rates[1], "evals_per_s_8_in_flight": rates[8],
+                     "pooled_values_bit_identical": same}
+    cb._lib.lib().cocons_release_workspace()
+    return out
+
+
 def north_star_single(local_rank, n_big, with_predict=False):
     """north_star: one full evaluation at n = 100 000 on ONE B200 (80 GB matrix), device-timed phases, Cholesky
     phase against the FP64 peak, and the sampled-entry residual of its factor against the reference covariance."""
@@ -582,6 +625,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     cpu = cpu_reference_sample(n) if world == 1 and not args.no_cpu_baseline else None
     big = north_star_single(local_rank, 100000, with_predict=True) if (world == 1 and not args.no_large) else None
+    small = reference_datasets_record(local_rank) if world == 1 else None
     line = {
         "metric": "neg2loglik evals/sec (assembly+Cholesky) at n=50k", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
@@ -620,6 +664,8 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if big is not None:
         line["north_star_n100k_1gpu"] = big
+    if small is not None:
+        line["reference_datasets"] = small
     if distributed is not None:
         line["distributed"] = distributed
     print(json.dumps(line))
