@@ -274,9 +274,13 @@ void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* win
 // Units are issued in the order of the front value they need (J1), last-chunk units first among equals: every
 // unit waits only for units with SMALLER tickets, which are already running or done - no deadlock for any
 // number of resident CTAs, so an ordinary launch suffices.  CTAs far behind the front stream L at full
-// bandwidth; the chain front -> L_{I,I-1} y_{I-1} -> W_I t -> front (two 128 x 128 products out of L2,
-// prefetched) is the critical path.  A dependency wait that does not end (a bug) sets ctrl[2] and ends the
-// kernel instead of hanging the device.
+// bandwidth (two batches of 16 loads in flight per thread); the chain front -> L_{I,I-1} y_{I-1} -> W_I t -> front
+// is the critical path and is kept short: the row-finishing unit holds its piece of L_{I,I-1} in registers before
+// the front arrives, picks y_{I-1} up element by element through an 'unset' bit pattern in Y (one L2 hop instead
+// of a flag hop followed by a data hop; Y is a scratch copy of the solution, B receives it too), and has the W_I
+// loads (prefetched to L2 when the unit starts) in flight during the reduction.  A dependency wait that does not
+// end (a bug) sets ctrl[2] and *info and ends the kernel instead of hanging the device.
+// Measured at n = 50 000, one right-hand side: 2.47 ms, 10.15 GB read = 4.1 TB/s (profiles/r02_kernels_ncu.md).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
