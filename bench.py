@@ -479,6 +479,34 @@ def distributed_record(torch, dist, dev, rank, world, n_large):
     return rec
 
 
+def cusolver_potrf_comparator(torch, dev, n):
+    """the library bar - torch.linalg.cholesky (cuSOLVER potrf, FP64) on an SPD matrix of the same
+    n.  Comparison only; nothing of it is on the product path."""
+    try:
+        g = torch.Generator(device=dev).manual_seed(1)
+        M = torch.randn(n, 64, dtype=torch.float64, device=dev, generator=g)
+        A = M @ M.T
+        A.diagonal().add_(float(n))
+        del M
+        best = None
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            Lc = torch.linalg.cholesky(A)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+            del Lc
+        del A
+        torch.cuda.empty_cache()
+        return {"routine": "torch.linalg.cholesky (cuSOLVER potrf), float64", "n": n, "ms": best,
+                "tflops": flops_chol(n) / (best * 1e-3) / 1e12}
+    except Exception as e:  # comparison only: never fail the bench for it
+        torch.cuda.empty_cache()
+        return {"routine": "torch.linalg.cholesky", "unavailable": str(e)[:200]}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -626,6 +654,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = cpu_reference_sample(n) if world == 1 and not args.no_cpu_baseline else None
     big = north_star_single(local_rank, 100000, with_predict=True) if (world == 1 and not args.no_large) else None
     small = reference_datasets_record(local_rank) if world == 1 else None
+    lib_cmp = cusolver_potrf_comparator(torch, dev, n) if (world == 1 and not args.no_large) else None
     line = {
         "metric": "neg2loglik evals/sec (assembly+Cholesky) at n=50k", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
@@ -666,6 +695,8 @@ def run_ours(args, rank, world, local_rank):
         line["north_star_n100k_1gpu"] = big
     if small is not None:
         line["reference_datasets"] = small
+    if lib_cmp is not None:
+        line["roofline"]["cholesky_phase"]["library_comparator"] = lib_cmp
     if distributed is not None:
         line["distributed"] = distributed
     print(json.dumps(line))
