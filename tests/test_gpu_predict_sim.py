@@ -23,7 +23,7 @@ def _setup(datasets, n, m):
     return H[:n, :2], sc["std.covs"], H[:n, 4], T[:m, :2].copy(), Xp
 
 
-@pytest.mark.parametrize("n,m", [(600, 150), (1000, 430)])
+@pytest.mark.parametrize("n,m", [(600, 150), (1000, 430), (5570, 430)])  # the last: BASELINE configs[0] at full size
 def test_predict_matches_reference_route(datasets, n, m):
     locs, X, z, lp, Xp = _setup(datasets, n, m)
     lp[7] = locs[11]  # a prediction site sitting on a training site

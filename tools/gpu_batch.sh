@@ -1,8 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1s.json 2> gpurun_out/r2_bench_n1s.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench_n1s.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2_bench_n1s.json').read().strip().splitlines()[-1])
-print(d['value'], d['roofline']['cholesky_phase'])
-"
+( time timeout 900 python -m pytest tests -x -q -m gpu -k "predict_matches" ) > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
