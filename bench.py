@@ -282,20 +282,36 @@ def golden_theta(case):
     return {k: np.array(v, dtype=np.float64) for k, v in case["theta"].items()}
 
 
-def sampled_factor_residual(ctx, locs, X, theta, m=48, seed=7):
-    """max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb) over all pairs of m sampled sites: L rows from the device
-    factor, Sigma from the oracle (the reference's compiled cov_rns on the m-site subset - an entry of cov_rns
-    depends on its two sites and theta only).  Size-independent check of assembly + factorisation."""
-    from oracle import cov
-    n = locs.shape[0]
-    rng = np.random.default_rng(seed)
-    sites = np.sort(rng.choice(n, m, replace=False))
+def north_star_problem(n_big):
+    """Data of the n_big-site north-star evaluation: the first n_big sites of one synthetic stream of n_big + n_big / 5
+    sites (the rest are the prediction sites of BASELINE configs[4]); theta = theta_at(0, 0)."""
+    m_pred = n_big // 5
+    locs_all, X_all, z_all = synthetic(n_big + m_pred)
+    return (np.asfortranarray(locs_all[:n_big]), np.asfortranarray(X_all[:n_big]), z_all[:n_big],
+            np.asfortranarray(locs_all[n_big:]), np.asfortranarray(X_all[n_big:]), theta_at(0, 0))
+
+
+def sampled_sites(n, m=48, seed=7):
+    return np.sort(np.random.default_rng(seed).choice(n, m, replace=False))
+
+
+def sampled_factor_residual(ctx, n_big):
+    """max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb) over all pairs of the sampled sites: L rows from the device
+    factor, Sigma from the committed fixture tests/golden/sigma_samples.npz (the reference's compiled cov_rns on
+    those sites, written by `python -m oracle.make_golden_large --sigma-samples`; an entry of cov_rns depends on its
+    two sites and theta only).  Size-independent check of assembly + factorisation; None without a fixture."""
+    try:
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "sigma_samples.npz"))
+        sites, S = fx["sites_n%d" % n_big], fx["sigma_n%d" % n_big]
+    except (OSError, KeyError):
+        return None
     rows, _ = ctx.factor_rows(sites)
     G = rows @ rows.T
-    kind = "reference" if cov.have_reference() else "restatement"
-    S = cov.cov_rns(theta, np.asfortranarray(locs[sites]), np.asfortranarray(X[sites]), LIMITS, kind=kind)
     d = np.sqrt(np.diag(S))
-    return float(np.max(np.abs(G - S) / np.outer(d, d))), kind, m
+    return {"max_rel": float(np.max(np.abs(G - S) / np.outer(d, d))), "sampled_sites": int(len(sites)),
+            "entries": int(len(sites) * (len(sites) + 1) // 2),
+            "sigma_from": "tests/golden/sigma_samples.npz (reference's compiled cov_rns)",
+            "what": "max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb)"}
 
 
 def reference_datasets_record(local_rank):
@@ -346,20 +362,17 @@ def north_star_single(local_rank, n_big, with_predict=False):
     phase against the FP64 peak, and the sampled-entry residual of its factor against the reference covariance."""
     import cocons_b200 as cb
     from cocons_b200 import _lib
-    m_pred = n_big // 5 if with_predict else 0
-    locs_all, X_all, z_all = synthetic(n_big + m_pred)  # one stream: the first n_big sites train, the rest predict
-    locs, X, z = np.asfortranarray(locs_all[:n_big]), np.asfortranarray(X_all[:n_big]), z_all[:n_big]
-    th = theta_at(0, 0)
+    locs, X, z, lp, Xp, th = north_star_problem(n_big)
+    m_pred = lp.shape[0]
     cfg4 = None
     with cb.DenseLikelihood(locs, X, z, device=local_rank) as ctx:
         t = ctx.terms(_lib.ML, th, LIMITS, th["mean"])
         tm = ctx.timings()
-        resid, kind, m = sampled_factor_residual(ctx, locs, X, th)
+        resid = sampled_factor_residual(ctx, n_big)
         if with_predict:
             # BASELINE.json configs[4]: cocoPredict (type "pred") for n/5 new sites and one cocoSim draw on the KEPT
             # factor (R/predict.R:136-183, R/sim.R:87-121), with size-independent checks
             import torch
-            lp, Xp = np.asfortranarray(locs_all[n_big:]), np.asfortranarray(X_all[n_big:])
             r = z - X @ th["mean"]
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -392,8 +405,7 @@ def north_star_single(local_rank, n_big, with_predict=False):
             "eval_ms": tm["total_ms"], "assembly_ms": tm["assembly_ms"], "factor_ms": tm["factor_ms"],
             "solve_ms": tm["solve_ms"], "chol_tflops": tf, "frac_of_derived_fp64_peak": tf / DERIVED_FP64_PEAK_TFLOPS,
             "value": n_big * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0]),
-            "factor_residual": {"max_rel": resid, "sampled_sites": m, "entries": m * (m + 1) // 2, "sigma_from": kind,
-                                "what": "max |(L L^T - Sigma)_ab| / sqrt(Sigma_aa Sigma_bb), Sigma_ab from the oracle"}}
+            "factor_residual": resid}
 
 
 def distributed_record(torch, dist, dev, rank, world, n_large):
@@ -448,7 +460,7 @@ def distributed_record(torch, dist, dev, rank, world, n_large):
     if rank == 0:
         single = north_star_single(dev.index, n_mid)
     dist.barrier()
-    locs, X, z = synthetic(n_mid)
+    locs, X, z = north_star_problem(n_mid)[:3]
     with DistributedDenseLikelihood(locs, X, z) as d:
         t = d.terms(_lib.ML, theta_at(0, 0), LIMITS, THETA["mean"])
         v_dist = n_mid * np.log(2 * np.pi) + 2 * t["logdet"] + float(t["quad"][0])

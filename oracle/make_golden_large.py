@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--workers", type=int, default=os.cpu_count())
     ap.add_argument("--check", action="store_true", help="block-pair assembly == one direct cov_rns call (n = 3000)")
     ap.add_argument("--check-blocked", action="store_true", help="blocked LAPACK route == one dpotrf (n = 20 000)")
+    ap.add_argument("--sigma-samples", default="", help="comma list of n: covariance of bench.sampled_sites(n) of "
+                    "bench.north_star_problem(n) by the reference's cov_rns -> tests/golden/sigma_samples.npz")
     args = ap.parse_args()
     import bench
     if args.check:
@@ -146,6 +148,19 @@ def main():
         same = np.array_equal(A[il], B[il])
         print("block-pair assembly bit-equal to the direct reference call (lower triangle, n=3000):", same)
         sys.exit(0 if same else 1)
+    if args.sigma_samples:
+        path = os.path.join(ROOT, "tests", "golden", "sigma_samples.npz")
+        out = dict(np.load(path)) if os.path.exists(path) else {}
+        for n in (int(x) for x in args.sigma_samples.split(",")):
+            locs, X, _, _, _, th = bench.north_star_problem(n)
+            sites = bench.sampled_sites(n)
+            out["sites_n%d" % n] = sites
+            out["sigma_n%d" % n] = cov.cov_rns(th, np.asfortranarray(locs[sites]), np.asfortranarray(X[sites]), LIMITS,
+                                               kind="reference")
+            print("n=%d: %d sites, Sigma diag %.4f..%.4f" % (n, len(sites), np.diag(out["sigma_n%d" % n]).min(),
+                                                          np.diag(out["sigma_n%d" % n]).max()))
+        np.savez(path, **out)
+        sys.exit(0)
     if args.check_blocked:
         locs, X, z = bench.synthetic(20000)
         th = point_theta("base")

@@ -120,12 +120,19 @@ def test_n50k_against_reference_golden_and_bit_reproducible():
 
 def test_sampled_entries_of_the_factor_reproduce_the_reference_covariance():
     """(L L^T)_ab for sampled sites against the reference's cov_rns on the same sites: a size-independent residual
-    check of assembly + factorisation (bench.py reports it at n = 100 000, where no CPU oracle can factor)."""
+    check of assembly + factorisation (bench.py reports it at n = 100 000, where no CPU oracle can factor, from the
+    committed fixture tests/golden/sigma_samples.npz)."""
+    from oracle import cov
     n = 20000
     locs, X, z = bench.synthetic(n)
     th = bench.theta_at(0, 0)
+    sites = bench.sampled_sites(n, m=64)
+    kind = "reference" if cov.have_reference() else "restatement"
+    S = cov.cov_rns(th, np.asfortranarray(locs[sites]), np.asfortranarray(X[sites]), bench.LIMITS, kind=kind)
     with cb.DenseLikelihood(locs, X, z) as ctx:
         ctx.terms(_lib.ML, th, bench.LIMITS, th["mean"])
-        resid, kind, m = bench.sampled_factor_residual(ctx, locs, X, th, m=64)
-    print("sampled factor residual at n=%d over %d sites (%s covariance): %.2e" % (n, m, kind, resid))
+        rows, _ = ctx.factor_rows(sites)
+    d = np.sqrt(np.diag(S))
+    resid = float(np.max(np.abs(rows @ rows.T - S) / np.outer(d, d)))
+    print("sampled factor residual at n=%d over %d sites (%s covariance): %.2e" % (n, len(sites), kind, resid))
     assert resid < 1e-11

@@ -8,6 +8,8 @@ asserts shapes / positive eigenvalues / absence of NA), so the pi
   * 40-digit mpmath evaluations of the mathematical formula;
   * closed forms, the stationary textbook Matern limit and the Profile/REML identities.
 """
+import os
+
 import mpmath as mp
 import numpy as np
 import pytest
@@ -213,3 +215,17 @@ def test_host_helpers():
     assert np.allclose(sc["std.covs"][:, 1].std(ddof=1), 1.0) and np.allclose(sc["std.covs"][:, 0], 1.0)
     assert rmirror.r_qr_rank(X) == 3
     assert rmirror.r_qr_rank(np.column_stack([X, X[:, 1] * 2])) == 3
+
+
+def test_sigma_sample_fixture_matches_the_oracle():
+    """The fixture bench.py checks its n = 100 000 factor against is what the oracle gives for those sites."""
+    import bench
+    from conftest import GOLD
+    fx = np.load(os.path.join(GOLD, "sigma_samples.npz"))
+    n = 100000
+    locs, X, _, _, _, th = bench.north_star_problem(n)
+    sites = bench.sampled_sites(n)
+    assert np.array_equal(fx["sites_n%d" % n], sites)
+    kind = "reference" if cov.have_reference() else "restatement"
+    S = cov.cov_rns(th, np.asfortranarray(locs[sites]), np.asfortranarray(X[sites]), bench.LIMITS, kind=kind)
+    assert np.array_equal(S, fx["sigma_n%d" % n])
