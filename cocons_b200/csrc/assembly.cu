@@ -174,7 +174,18 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
   __shared__ double cs[11][kAsmTile];
   __shared__ int corig[kAsmTile];
   int tr, tc;
-  if (slab) {
+  if (slab >= 2) {
+    // slab = 2 + 16 (world + 64 rank): C holds ALL column panels of one rank of the block-cyclic layout (csrc/dist.cu:
+    // 4-tile panels dealt in a snake), back to back; blockIdx.y is the local tile column, blockIdx.x the tile row.
+    // One launch per evaluation instead of one per panel (98 launches of ~1.3 waves each at n = 50 000).
+    const int world = (slab >> 4) & 63, rank = slab >> 10;
+    const int lc = blockIdx.y, lp = lc >> 2;
+    const int K = lp * world + ((lp & 1) ? world - 1 - rank : rank);
+    tc = K * 4 + (lc & 3);
+    tr = blockIdx.x;
+    if (tr < tc || (int64_t)tc * kAsmTile >= n_out) return;
+    C += ((int64_t)lc - tc) * kAsmTile * ld;
+  } else if (slab) {
     tr = col_tile0 + blockIdx.x;
     tc = col_tile0 + blockIdx.y;
     if (tr < tc) return;
@@ -397,6 +408,15 @@ void launch_assemble_panel(int64_t n, int64_t n_out, SiteTable T, double global_
   const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
   launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, slab, ld, col_tile0, 1,
                       dim3((unsigned)(nt - col_tile0), (unsigned)ncol_tiles), st);
+}
+
+// all column panels of one rank of the block-cyclic layout (nlocal panels of 4 tile columns, back to back in `slab`)
+void launch_assemble_cyclic(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                            double* slab, int64_t ld, int world, int rank, int64_t nlocal, cudaStream_t st) {
+  const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
+  if (nlocal <= 0 || world > 63) return;
+  launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, slab, ld, 0, 2 | (world << 4) | (rank << 10),
+                      dim3((unsigned)nt, (unsigned)(nlocal * 4)), st);
 }
 
 static void launch_assemble_any(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,

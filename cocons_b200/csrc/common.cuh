@@ -69,6 +69,8 @@ void launch_assemble_lower(int64_t n, int64_t n_out, SiteTable T, double global_
                            double* C, int64_t ld, cudaStream_t st);
 void launch_assemble_panel(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
                            double* slab, int64_t ld, int col_tile0, int ncol_tiles, cudaStream_t st);
+void launch_assemble_cyclic(int64_t n, int64_t n_out, SiteTable T, double global_range, double nu_fixed, int mode,
+                            double* slab, int64_t ld, int world, int rank, int64_t nlocal, cudaStream_t st);
 void launch_assemble_cross(int64_t m, int64_t n, SiteTable Tpred, SiteTable Ttrain, double global_range, double* C,
                            int64_t ld, cudaStream_t st);
 void launch_symmetrize(int64_t n, double* C, int64_t ld, cudaStream_t st);
