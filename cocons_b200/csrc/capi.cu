@@ -1263,6 +1263,15 @@ int cocons_ctx_factor_rows(cocons_ctx* c, const int64_t* sites, int64_t m, doubl
   return 0;
 }
 
+int64_t cocons_debug_solve_units(int64_t n_pad, int32_t* units4, int64_t capacity) {
+  if (n_pad <= 0 || n_pad % kTile) return COCONS_ERR_ARG;
+  std::vector<int> u;
+  const int64_t count = build_solve_units(n_pad / kTile, &u);
+  if (units4)
+    for (int64_t i = 0; i < 4 * count && i < 4 * capacity; ++i) units4[i] = u[(size_t)i];
+  return count;
+}
+
 int cocons_ctx_timings(cocons_ctx* c, double* ms4) {
   if (!c || !ms4) return COCONS_ERR_ARG;
   for (int i = 0; i < 4; ++i) ms4[i] = c->ms[i];

@@ -133,6 +133,10 @@ void launch_logdet(const double* L, int64_t n, int64_t ld, double* out, cudaStre
 void forward_solve(const double* L, int64_t n_pad, int64_t ld, const double* winv, double* B, int64_t ldb, int nrhs,
                    cudaStream_t st);
 int solve_workspace_create(int64_t n_pad, CholWorkspace* ws);
+}  // namespace cocons
+#include <vector>
+namespace cocons {
+int build_solve_units(int64_t T, std::vector<int>* out);  // host: work units of the dataflow substitution, issue order
 void solve_workspace_destroy(CholWorkspace* ws);
 // L Y = B with the dataflow kernel when ws carries a solve workspace (else the cooperative kernel above); a
 // stalled dependency wait (which would be a bug) is reported through *info_dev = COCONS_ERR_CUDA instead of hanging

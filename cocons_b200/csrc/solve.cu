@@ -540,9 +540,11 @@ __global__ void __launch_bounds__(256, (NR == 1) ? 2 : 1)
   }
 }
 
-int solve_workspace_create(int64_t n_pad, CholWorkspace* ws) {
-  const int T = (int)(n_pad / kTile);
-  const int nchunks = (T - 1 + kSolveChunk - 1) / kSolveChunk > 0 ? (T - 1 + kSolveChunk - 1) / kSolveChunk : 1;
+// The work units of the dataflow substitution for T tile rows, in issue order: 4 ints per unit (tile row I, first
+// tile column J0, end J1, chunk index).  Issue order = the front value a unit needs (J1); among equals the
+// row-finishing units (J1 == I) first, then by row - so every unit depends only on units issued before it.
+// Host-only; also reachable through cocons_debug_solve_units for the CPU test of exactly that property.
+int build_solve_units(int64_t T, std::vector<int>* out) {
   struct Unit {
     int I, J0, J1, ch;
   };
@@ -551,21 +553,31 @@ int solve_workspace_create(int64_t n_pad, CholWorkspace* ws) {
   for (int I = 1; I < T; ++I)
     for (int ch = 0; ch * kSolveChunk < I; ++ch)
       units.push_back({I, ch * kSolveChunk, std::min((ch + 1) * kSolveChunk, I), ch});
-  // issue order: by the front value a unit needs (J1); among equals the row-finishing units first, then by row
   std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) {
     if (a.J1 != b.J1) return a.J1 < b.J1;
     const bool fa = a.J1 == a.I, fb = b.J1 == b.I;
     if (fa != fb) return fa;
     return a.I < b.I;
   });
-  ws->solve_nunits = (int)units.size(), ws->solve_nchunks = nchunks;
+  out->clear();
+  for (const Unit& u : units) out->insert(out->end(), {u.I, u.J0, u.J1, u.ch});
+  return (int)units.size();
+}
+
+int solve_workspace_create(int64_t n_pad, CholWorkspace* ws) {
+  const int T = (int)(n_pad / kTile);
+  const int nchunks = (T - 1 + kSolveChunk - 1) / kSolveChunk > 0 ? (T - 1 + kSolveChunk - 1) / kSolveChunk : 1;
+  std::vector<int> units;
+  build_solve_units(T, &units);
+  const size_t nunits = units.size() / 4;
+  ws->solve_nunits = (int)nunits, ws->solve_nchunks = nchunks;
   if (cudaMalloc(&ws->solve_ctrl, sizeof(unsigned) * (4 + (size_t)T)) != cudaSuccess ||
-      cudaMalloc(&ws->solve_units, sizeof(int) * 4 * units.size()) != cudaSuccess ||
+      cudaMalloc(&ws->solve_units, sizeof(int) * units.size()) != cudaSuccess ||
       cudaMalloc(&ws->solve_part, sizeof(double) * (size_t)T * nchunks * kSolveMaxRhs * kTile) != cudaSuccess) {
     solve_workspace_destroy(ws);
     return COCONS_ERR_ALLOC;
   }
-  if (cudaMemcpy(ws->solve_units, units.data(), sizeof(int) * 4 * units.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMemcpy(ws->solve_units, units.data(), sizeof(int) * units.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     solve_workspace_destroy(ws);
     return COCONS_ERR_CUDA;
   }

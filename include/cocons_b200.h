@@ -195,6 +195,11 @@ int cocons_ctx_get_factor(cocons_ctx* ctx, double* L, int64_t* perm);
  * whose full factor does not fit a host (n = 100 000: 80 GB). */
 int cocons_ctx_factor_rows(cocons_ctx* ctx, const int64_t* sites, int64_t m, double* rows, int64_t* pos);
 
+/* Host only, for tests: the work units of the forward substitution (csrc/solve.cu, K6b) for an n_pad x n_pad factor, in
+ * issue order, 4 ints each (tile row, first tile column, end tile column, chunk).  Returns their number (units4 may be
+ * NULL); no device is touched.  (forwardsolve, R/neg2loglikelihood.R:214-217) */
+int64_t cocons_debug_solve_units(int64_t n_pad, int32_t* units4, int64_t capacity);
+
 /* per-phase device times of the last evaluation, milliseconds (CUDA events on
  * the context's stream): [0] site+assembly [1] factorisation [2] solves+reductions [3] total */
 int cocons_ctx_timings(cocons_ctx* ctx, double* ms4);

@@ -270,3 +270,51 @@ def test_trapezoid_band_of_the_device_bessel_against_mpmath(tmp_path):
             ref = mp.besselk(mp.mpf(float(nu)), mp.mpf(float(x))) * mp.e ** mp.mpf(float(x))
             worst = max(worst, float(abs((mp.mpf(lib.h_t(float(nu), float(x))) - ref) / ref)))
     assert worst < 2.5e-15, worst
+
+
+@pytest.mark.parametrize("n_pad", [128, 256, 2176, 5632, 12032, 50048])
+def test_forward_substitution_work_units_cover_the_factor_and_are_issued_in_dependency_order(n_pad):
+    """The dataflow forward substitution (csrc/solve.cu, K6b) hands its work units to CTAs through a ticket
+    counter; it cannot deadlock, for any number of resident CTAs, iff every unit depends only on units with
+    smaller tickets.  Host-side check of the unit table: the chunks of a row tile [0, I) exactly once, the last
+    chunk of a row is the one that finishes it, and for every unit the row-finishing units of all rows below
+    its end column J1 (the y it consumes) come earlier in the issue order."""
+    L = _lib.lib()
+    count = L.cocons_debug_solve_units(n_pad, None, 0)
+    T = n_pad // 128
+    u = np.zeros((count, 4), dtype=np.int32)
+    assert L.cocons_debug_solve_units(n_pad, u.ctypes.data_as(_lib._i32p), count) == count
+    finisher = {}  # row -> ticket of its row-finishing unit
+    covered = {I: [] for I in range(T)}
+    for ticket, (I, J0, J1, ch) in enumerate(u):
+        assert 0 <= J0 <= J1 <= I < T and J1 - J0 <= 16
+        covered[int(I)].append((int(J0), int(J1), int(ch)))
+        if J1 == I:
+            assert int(I) not in finisher
+            finisher[int(I)] = ticket
+    assert sorted(finisher) == list(range(T))
+    for I, chunks in covered.items():
+        chunks.sort()
+        assert [c[2] for c in chunks] == list(range(len(chunks)))          # chunk indices 0..k in column order
+        edges = [c[0] for c in chunks] + [chunks[-1][1]]
+        assert edges[0] == 0 and edges[-1] == I and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+    first_needed = np.array([finisher[r] for r in range(T)])
+    for ticket, (I, J0, J1, ch) in enumerate(u):
+        if J1 > 0:  # consumes y_0 .. y_{J1 - 1}: all of them finished by earlier tickets
+            assert first_needed[:J1].max() < ticket, (ticket, I, J0, J1)
+        if J1 == I and ch > 0:  # the finisher also waits for the row's other chunks
+            others = [t for t, (I2, _, J12, _) in enumerate(u) if I2 == I and J12 != I] if T <= 48 else None
+            if others is not None:
+                assert max(others) < ticket
+
+
+def test_trailing_update_tile_numbering_is_a_bijection(tmp_path):
+    """csrc/chol.cu numbers the tiles of a (lower-trapezoid) update band by band and a CTA decodes its tile in
+    O(1) (tile_decode): exhaustive host check over ~35 000 shapes that the decode is a bijection onto the
+    expected tile set (tools/micro/tile_decode_check.cu; the functions are __host__ __device__, no kernel runs)."""
+    exe = tmp_path / "tile_decode_check"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                           os.path.join(ROOT, "tools", "micro", "tile_decode_check.cu"), "-o", str(exe)],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and " 0 wrong" in out.stdout, out.stdout
