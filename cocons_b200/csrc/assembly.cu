@@ -397,7 +397,13 @@ void launch_assemble_lower(int64_t n, int64_t n_out, SiteTable T, double global_
                            double* C, int64_t ld, cudaStream_t st) {
   const int64_t nt = (n_out + kAsmTile - 1) / kAsmTile;
   const int64_t tiles = nt * (nt + 1) / 2;
-  const unsigned slices = tiles < 2400 ? 8u : (tiles < 9600 ? 4u : 1u);  // ~1200 CTAs fit the GPU at once
+  // ~1200 CTAs fit the GPU at once; measured: holes (990 tiles) 2 / 4 / 8 / 16 / 32 slices -> 1.15 / 0.99 / 0.91 /
+  // 0.87 / 0.89 ms, stripes (4465 tiles) -> 3.58 / 3.45 / 3.41 / 3.46 / 3.59 ms
+  unsigned slices = tiles < 1500 ? 16u : (tiles < 6000 ? 8u : (tiles < 9600 ? 4u : 1u));
+  if (const char* e = getenv("COCONS_ASM_SLICES")) {  // experiment knob: 1, 2, 4, 8, 16, 32
+    const int v = atoi(e);
+    if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) slices = (unsigned)v;
+  }
   launch_assemble_any(n, n_out, T, global_range, nu_fixed, mode, C, ld, 0, 0, dim3((unsigned)tiles, 1, slices), st);
 }
 
