@@ -82,8 +82,15 @@ __global__ void __launch_bounds__(128) site_stage_kernel(int64_t n, int64_t n_fi
   T.fw(SF_P12)[s] = p12;
   T.fw(SF_E12)[s] = __fma_rn(ra, cs, -p12);
   T.fw(SF_NU)[s] = snu;
-  T.fw(SF_SIG)[s] = link_exp(e_sig);
-  T.fw(SF_W)[s] = __dmul_rn(D, sn);
+  // amplitude factor of the site: sigma_i sqrt(D_i sin t_i).  The reference forms
+  // corr sigma_i sigma_j sqrt(D_i sin t_i D_j sin t_j) / sqrt(det) per pair (:295-297); hoisting the square root
+  // to the site moves an entry by a few ulp (no amplification here, unlike Q) and takes two square roots and a
+  // division out of the pair loop.  SF_SIG / SF_W stay in the table for the entries that end up near the
+  // subnormal range, where the reference's own sequence of roundings is followed (pair_cov).
+  const double sig = link_exp(e_sig), w = __dmul_rn(D, sn);
+  T.fw(SF_SIG)[s] = sig;
+  T.fw(SF_W)[s] = w;
+  T.fw(SF_AMP)[s] = __dmul_rn(sig, __dsqrt_rn(w));
   T.fw(SF_DV)[s] = __dadd_rn(link_exp(e_var), link_exp(e_nug));  // :111
 }
 
@@ -93,15 +100,19 @@ __global__ void __launch_bounds__(128) site_stage_kernel(int64_t n, int64_t n_fi
 // (P, e) = (rnd(c d), c d - rnd(c d)).
 // ---------------------------------------------------------------------------
 struct SiteA {
-  double x, y, r, a2, ra, cs, nu, sig, w, dv;
+  double x, y, r, a2, ra, cs, nu, amp, dv;
 };
 struct SiteB {
-  double x, y, r, p22, e22, p12, e12, nu, sig, w;
+  double x, y, r, p22, e22, p12, e12, nu, amp;
 };
 
-template <int MODE>
+// Correlations below this go through `slow_amp` (the reference's operation order on sigma and D sin t read back
+// from the site table): their entries may be subnormal, where every intermediate rounding of the reference shows.
+constexpr double kTinyCorr = 1e-250;
+
+template <int MODE, class SlowAmp>
 __device__ __forceinline__ double pair_cov(const SiteA& a, const SiteB& b, double global_range, double nu_fixed,
-                                           bool& coincident) {
+                                           bool& coincident, SlowAmp slow_amp) {
   // sigma11, sigma22, sigma12 of the averaged kernel matrix (:260-268)
   const double s11 = __dmul_rn(__dadd_rn(a.r, b.r), 0.5);
   const double s22 = __dmul_rn(__dadd_rn(__fma_rn(a.r, a.a2, b.p22), b.e22), 0.5);
@@ -138,9 +149,16 @@ __device__ __forceinline__ double pair_cov(const SiteA& a, const SiteB& b, doubl
   } else {
     corr = (Q < 706.0) ? matern_corr(nu, Q) : matern_corr_tail(nu, Q);  // :291-305
   }
-  // corr * sigma_i * sigma_j * sqrt(D_i sin t_i D_j sin t_j) / sqrt(det), left to right (:295-297)
-  const double amp = __dmul_rn(__dmul_rn(corr, a.sig), b.sig);
-  return __ddiv_rn(__dmul_rn(amp, __dsqrt_rn(__dmul_rn(a.w, b.w))), __dsqrt_rn(det));
+  // corr * sigma_i * sigma_j * sqrt(D_i sin t_i D_j sin t_j) / sqrt(det) (:295-297) with the per-site parts hoisted
+  if (!(fabs(corr) >= kTinyCorr)) return slow_amp(corr, det);
+  return __dmul_rn(__dmul_rn(corr, __dmul_rn(a.amp, b.amp)), rsqrt(det));
+}
+
+// the amplitude in the reference's order, left to right (:295-297); sa / wa belong to the "ii" site
+__device__ __noinline__ double amp_reference_order(double corr, double det, double sa, double sb, double wa,
+                                                   double wb) {
+  const double amp = __dmul_rn(__dmul_rn(corr, sa), sb);
+  return __ddiv_rn(__dmul_rn(amp, __dsqrt_rn(__dmul_rn(wa, wb))), __dsqrt_rn(det));
 }
 
 // ---------------------------------------------------------------------------
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
   // slab == 0: C is the whole matrix, blockIdx.x runs over its lower-triangle tiles.
   // slab == 1: C holds only the tile columns [col_tile0, col_tile0 + gridDim.y) (a column panel of a
   //            distributed matrix); blockIdx.x runs over the tile rows from col_tile0 down.
-  __shared__ double cs[11][kAsmTile];
+  __shared__ double cs[9][kAsmTile];
   __shared__ int corig[kAsmTile];
   int tr, tc;
   if (slab >= 2) {
@@ -206,9 +224,8 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
     cs[4][tid] = ok ? T.f(SF_RA)[J] : 1.0;
     cs[5][tid] = ok ? T.f(SF_CS)[J] : 0.0;
     cs[6][tid] = ok ? T.f(SF_NU)[J] : 1.0;
-    cs[7][tid] = ok ? T.f(SF_SIG)[J] : 0.0;
-    cs[8][tid] = ok ? T.f(SF_W)[J] : 0.0;
-    cs[9][tid] = ok ? T.f(SF_DV)[J] : 1.0;
+    cs[7][tid] = ok ? T.f(SF_AMP)[J] : 0.0;
+    cs[8][tid] = ok ? T.f(SF_DV)[J] : 1.0;
     corig[tid] = (ok && T.orig) ? T.orig[J] : (int)J;
   }
   SiteB b;
@@ -224,8 +241,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
     b.p12 = T.f(SF_P12)[I];
     b.e12 = T.f(SF_E12)[I];
     b.nu = T.f(SF_NU)[I];
-    b.sig = T.f(SF_SIG)[I];
-    b.w = T.f(SF_W)[I];
+    b.amp = T.f(SF_AMP)[I];
     dvI = T.f(SF_DV)[I];
     if (T.orig) origI = T.orig[I];
   } else {
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
     b.r = b.p22 = b.p12 = 1.0;
     b.e22 = b.e12 = 0.0;
     b.nu = 1.0;
-    b.sig = b.w = 0.0;
+    b.amp = 0.0;
   }
   __syncthreads();
   if (I >= n_out) return;
@@ -260,11 +276,12 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
       a.ra = cs[4][j];
       a.cs = cs[5][j];
       a.nu = cs[6][j];
-      a.sig = cs[7][j];
-      a.w = cs[8][j];
-      a.dv = cs[9][j];
+      a.amp = cs[7][j];
+      a.dv = cs[8][j];
       bool coincident;
-      v = pair_cov<MODE>(a, b, global_range, nu_fixed, coincident);
+      v = pair_cov<MODE>(a, b, global_range, nu_fixed, coincident, [&](double corr, double det) {
+        return amp_reference_order(corr, det, T.f(SF_SIG)[J], T.f(SF_SIG)[I], T.f(SF_W)[J], T.f(SF_W)[I]);
+      });
       // :284-286 - the value of the lower caller-order index of the pair
       if (coincident) v = (corig[j] < origI) ? a.dv : dvI;
     }
@@ -281,7 +298,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
 __global__ void __launch_bounds__(kAsmTile) assemble_cross_kernel(int64_t m, int64_t n, SiteTable P, SiteTable T,
                                                                   double global_range, double* __restrict__ C,
                                                                   int64_t ld) {
-  __shared__ double cs[10][kAsmTile];
+  __shared__ double cs[9][kAsmTile];
   const int tid = threadIdx.x;
   const int64_t I = (int64_t)blockIdx.x * kAsmTile + tid;
   const int64_t J0 = (int64_t)blockIdx.y * kAsmTile;
@@ -296,8 +313,7 @@ __global__ void __launch_bounds__(kAsmTile) assemble_cross_kernel(int64_t m, int
     cs[5][tid] = ok ? T.f(SF_P12)[J] : 1.0;
     cs[6][tid] = ok ? T.f(SF_E12)[J] : 0.0;
     cs[7][tid] = ok ? T.f(SF_NU)[J] : 1.0;
-    cs[8][tid] = ok ? T.f(SF_SIG)[J] : 0.0;
-    cs[9][tid] = ok ? T.f(SF_W)[J] : 0.0;
+    cs[8][tid] = ok ? T.f(SF_AMP)[J] : 0.0;
   }
   SiteA a;
   const bool rowok = I < m;
@@ -309,8 +325,7 @@ __global__ void __launch_bounds__(kAsmTile) assemble_cross_kernel(int64_t m, int
     a.ra = P.f(SF_RA)[I];
     a.cs = P.f(SF_CS)[I];
     a.nu = P.f(SF_NU)[I];
-    a.sig = P.f(SF_SIG)[I];
-    a.w = P.f(SF_W)[I];
+    a.amp = P.f(SF_AMP)[I];
     a.dv = P.f(SF_DV)[I];
   }
   __syncthreads();
@@ -326,14 +341,15 @@ __global__ void __launch_bounds__(kAsmTile) assemble_cross_kernel(int64_t m, int
     b.p12 = cs[5][j];
     b.e12 = cs[6][j];
     b.nu = cs[7][j];
-    b.sig = cs[8][j];
-    b.w = cs[9][j];
+    b.amp = cs[8][j];
     double v;
     if (a.x == b.x && a.y == b.y) {  // :410
       v = a.dv;
     } else {
       bool coincident;
-      v = pair_cov<SM_GENERAL>(a, b, global_range, 0.0, coincident);
+      v = pair_cov<SM_GENERAL>(a, b, global_range, 0.0, coincident, [&](double corr, double det) {
+        return amp_reference_order(corr, det, P.f(SF_SIG)[I], T.f(SF_SIG)[J0 + j], P.f(SF_W)[I], T.f(SF_W)[J0 + j]);
+      });
       if (coincident) v = a.dv;  // :440-442
     }
     C[(J0 + j) * ld + I] = v;

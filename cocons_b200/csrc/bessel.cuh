@@ -25,6 +25,7 @@
 #endif
 
 #include "gamma_coeffs.inc"
+#include "log_table.inc"
 
 namespace cocons {
 
@@ -57,14 +58,22 @@ __device__
         1.6817928305074290861, 1.7186192981224779156, 1.7562521603732994831, 1.7947090750031071864,
         1.8340080864093424635, 1.8741676341102999013, 1.9152065613971472939, 1.957144124175400269};
 
-COCONS_HD double exp_poly(double y) {
-  if (y < -708.0) return 0.0;
+// Constants of the hot loops are chosen so that ptxas can encode them as 32-bit immediates (a double whose low
+// word is zero) wherever the arithmetic allows it - every other 64-bit literal costs two UMOV issue slots per
+// use, and the per-node body of the trapezoidal rule was 28 non-FP64 instructions against 19 FP64 ones:
+//   * 32 log2(e) only picks N, r is formed exactly whatever N is: 21 significant bits suffice;
+//   * ln2/32 = hi + lo with a 21-bit hi (fn hi is exact for |N| < 2^32) and a full-precision lo;
+//   * 1/120 and 1/720 multiply r^5 and r^6 (|r| <= 0.0109): rounding them to 21 bits moves e^r by < 1e-18.
+// ylo: a correction to the argument (|ylo| << 1) added after the reduction, where it is not lost to the rounding of y.
+template <bool kCheckUnderflow>
+COCONS_HD double exp_poly_impl(double y, double ylo = 0.0) {
+  if (kCheckUnderflow && y < -708.0) return 0.0;
   const double kMagic = 6755399441055744.0;  // 2^52 + 2^51: the low word of 32 y log2(e) + kMagic is N
-  const double t = fma(y, 46.166241308446829036, kMagic);
+  const double t = fma(y, 0x1.71547p+5, kMagic);
   const double fn = t - kMagic;
-  double r = fma(fn, -0.02166084938653512, y);  // ln2/32, upper 32 bits: fn * hi is exact
-  r = fma(fn, -5.9631716539705866e-12, r);
-  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  double r = fma(fn, -0x1.62e42p-6, y);          // exact
+  r = fma(fn, -0x1.fdf473de6af28p-27, r) + ylo;
+  double q = fma(r, 0x1.6c16cp-10, 0x1.11111p-7);
   q = fma(q, r, 1.0 / 24.0);
   q = fma(q, r, 1.0 / 6.0);
   q = fma(q, r, 0.5);
@@ -78,6 +87,77 @@ COCONS_HD double exp_poly(double y) {
   const long long N = (long long)fn;
   const double T = kExp2Tab[N & 31];
   return ldexp(fma(T, p, T), (int)(N >> 5));
+#endif
+}
+
+COCONS_HD double exp_poly(double y) { return exp_poly_impl<true>(y); }
+COCONS_HD double exp_poly2(double y, double ylo) { return exp_poly_impl<true>(y, ylo); }
+// for arguments known to stay above -708 (the nodes of the trapezoidal rule: the loop leaves long before)
+COCONS_HD double exp_poly_nocheck(double y) { return exp_poly_impl<false>(y); }
+
+
+// ln(x) = H + L (unevaluated sum, |L| << |H| or both tiny) for normal positive x, absolute error < 1e-18.
+// x = 2^e m, m in [1, 2); j = the top six mantissa bits pick c_j = 1 + (j + 1/2)/64 and the table gives
+// 1/c_j and -ln(1/c_j) = hi_j + lo_j (gen_log_table.py); r = m/c_j - 1 (one fma, |r| < 0.0078) and
+// ln(1 + r) = r + r^2 (-1/2 + r/3 - ... - r^6/8)  (next term 1e-20).  e ln2_hi + hi_j is exact (both multiples
+// of 2^-40), its sum with r goes through a two-sum, everything small is collected in L.  21 FP64 instructions
+// and two table loads; the library log (one double, 0.5 ulp: 4e-16 absolute at ln 350) needs ~75 instructions,
+// 18 of them UMOVs.  The Matern factor multiplies this by nu and exponentiates, so what counts is the
+// ABSOLUTE error, and the H + L form removes the rounding of the logarithm from the result altogether.
+#ifdef __CUDACC__
+__device__
+#endif
+    static const double kLogTabA[128]
+#ifdef __CUDACC__
+    __attribute__((aligned(16)))
+#endif
+    = COCONS_LOG_TAB_A;
+#ifdef __CUDACC__
+__device__
+#endif
+    static const double kLogTabB[64] = COCONS_LOG_TAB_B;
+
+COCONS_HD void log_hl(double x, double& H, double& L) {
+#ifdef __CUDA_ARCH__
+  const int hx = __double2hiint(x);
+  const int j = (hx >> 14) & 63;
+  const double e = (double)((hx >> 20) - 1023);
+  const double m = __hiloint2double((hx & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = __ldg(reinterpret_cast<const double2*>(kLogTabA) + j);
+  const double inv = t.x, thi = t.y, tlo = __ldg(&kLogTabB[j]);
+#else
+  int ex;
+  const double m = 2.0 * frexp(x, &ex);  // [1, 2)
+  const double e = (double)(ex - 1);
+  const int j = (int)((m - 1.0) * 64.0);
+  const double inv = kLogTabA[2 * j], thi = kLogTabA[2 * j + 1], tlo = kLogTabB[j];
+#endif
+  const double r = fma(m, inv, -1.0);
+  double p = fma(r, -0.125, 0x1.24925p-3);  // -1/8, 1/7 (21 bits: the term is < 3e-16)
+  p = fma(p, r, -0x1.55555p-3);             // -1/6 (21 bits)
+  p = fma(p, r, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double q = (r * r) * p;
+  const double h0 = fma(e, COCONS_LN2_HI, thi);  // exact
+  const double s = h0 + r;
+  const double bb = s - h0;
+  const double err = (h0 - (s - bb)) + (r - bb);
+  H = s;
+  L = (fma(e, COCONS_LN2_LO, tlo) + err) + q;
+}
+
+// 1/d for a normal d away from the ends of the exponent range, ~1 ulp: the hardware seed (20 bits) and two
+// Newton steps - 5 instructions where the IEEE division is ~22 with its range check and slow path
+COCONS_HD double rcp_fast(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  return fma(r, fma(-d, r, 1.0), r);
+#else
+  return 1.0 / d;
 #endif
 }
 
@@ -107,9 +187,13 @@ COCONS_HD TemmeGammas temme_gammas(double mu) {
 // 1/Gamma(nu) for nu = nl + mu, nu > 0, from 1/Gamma(1+mu)
 COCONS_HD double rgamma_from(double rgp, double mu, int nl) {
   if (nl == 0) return rgp * mu;  // Gamma(mu) = Gamma(1+mu)/mu
-  double prod = 1.0;
-  for (int k = 1; k < nl; ++k) prod *= (mu + (double)k);
-  return rgp / prod;
+  if (nl == 1) return rgp;
+  // (mu + 1)(mu + 2)... in the order of the plain loop; straight-line up to nu < 4.5
+  double prod = mu + 1.0;
+  if (nl > 2) prod *= mu + 2.0;
+  if (nl > 3) prod *= mu + 3.0;
+  for (int k = 4; k < nl; ++k) prod *= (mu + (double)k);
+  return rgp * rcp_fast(prod);
 }
 
 // K_mu(x), K_{mu+1}(x), UNSCALED, for 0 < x <= 2, |mu| <= 1/2  (Temme's series)
@@ -229,8 +313,9 @@ static const
 COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
   // sinh(a), a = nu h / 2 <= 0.47: odd series to a^15 (next term 2e-18 relative)
   const double a = 0.5 * kTrapH * nu, a2 = a * a;
-  double sh = fma(a2, 1.0 / 1307674368000.0, 1.0 / 6227020800.0);
-  sh = fma(sh, a2, 1.0 / 39916800.0);
+  // (the three highest coefficients rounded to 21 bits - immediates, see exp_poly - move sinh by < 2e-17 relative)
+  double sh = fma(a2, 0x1.ae7f4p-41, 0x1.61246p-33);
+  sh = fma(sh, a2, 0x1.ae645p-26);
   sh = fma(sh, a2, 1.0 / 362880.0);
   sh = fma(sh, a2, 1.0 / 5040.0);
   sh = fma(sh, a2, 1.0 / 120.0);
@@ -249,10 +334,10 @@ COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
 #pragma unroll
 #endif
   for (int k = 1; k < kTrapNodes - 1; k += 2) {
-    const double t1 = exp_poly(nx * kTrapC[k]) * C;
+    const double t1 = exp_poly_nocheck(nx * kTrapC[k]) * C;
     D = fma(delta, C, D);
     C += D;
-    const double t2 = exp_poly(nx * kTrapC[k + 1]) * C;
+    const double t2 = exp_poly_nocheck(nx * kTrapC[k + 1]) * C;
     sum += t1 + t2;
     if (t2 < 1e-17 * sum) break;
     D = fma(delta, C, D);
@@ -297,7 +382,7 @@ static const
 
 COCONS_HD double bessel_k_hankel_scaled(double nu, double x) {
   const double four_nu2 = 4.0 * nu * nu;
-  const double rx = 1.0 / x;
+  const double rx = rcp_fast(x);
   double term = 1.0, sum = 1.0;
 #pragma unroll
   for (int k = 0; k < kHankelTerms; k += 2) {
@@ -306,7 +391,7 @@ COCONS_HD double bessel_k_hankel_scaled(double nu, double x) {
     sum += t1 + term;
     if (fabs(term) < 1e-17 * fabs(sum) && fabs(t1) < 1e-17 * fabs(sum)) break;
   }
-  return sqrt(kHalfPi / x) * sum;
+  return sqrt(kHalfPi * rx) * sum;
 }
 
 // upward recurrence K_{mu+k+1} = K_{mu+k-1} + 2(mu+k)/x K_{mu+k}, nl steps
@@ -355,12 +440,22 @@ COCONS_HD double matern_corr(double nu, double Q) {
   const double mu = nu - (double)nl;
   const TemmeGammas G = temme_gammas(mu);
   const double two_rgamma = 2.0 * rgamma_from(G.rgp, mu, nl);
-  const double powfac = exp_poly(nu * log(0.5 * Q));  // (Q/2)^nu
   const int band = bessel_band(nu, Q);
+  // (Q/2)^nu e^{-Q} (x > 2: the Bessel bodies return e^x K) or (Q/2)^nu (Temme band, unscaled K) from ONE
+  // exponential: nu (H + L) - Q is formed as a two-term sum, so neither the rounding of the logarithm nor that
+  // of the difference reaches the result
+  double H, L;
+  log_hl(0.5 * Q, H, L);
+  const double sub = (band == 0) ? 0.0 : Q;
+  const double p = nu * H;
+  const double s = p - sub;
+  const double bb = s - p;
+  const double lo = fma(nu, L, fma(nu, H, -p) + ((p - (s - bb)) - (sub + bb)));
+  const double scale = exp_poly2(s, lo);
   if (band == 0) {
     double kmu, kmu1;
     bessel_k_temme(mu, Q, G, kmu, kmu1);
-    return two_rgamma * powfac * bessel_k_recur(kmu, kmu1, mu, Q, nl);
+    return two_rgamma * scale * bessel_k_recur(kmu, kmu1, mu, Q, nl);
   }
   double ks;
   if (band == 2) {
@@ -372,7 +467,7 @@ COCONS_HD double matern_corr(double nu, double Q) {
     bessel_k_cf2_scaled(mu, Q, kmu, kmu1);
     ks = bessel_k_recur(kmu, kmu1, mu, Q, nl);
   }
-  return two_rgamma * powfac * ks * exp_poly(-Q);
+  return two_rgamma * ks * scale;
 }
 
 // The reference's own tail formula for Q >= 706 (src/cocons_full.cpp:299-305):

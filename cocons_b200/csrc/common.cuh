@@ -26,6 +26,7 @@ enum SiteField {
   SF_NU,     // smooth_vector (sqrt of the logistic, or exp() for classic)
   SF_SIG,    // sigma_vector   = E(0.5 std.dev)
   SF_W,      // dets_vector * sin(tilt)
+  SF_AMP,    // SF_SIG * sqrt(SF_W): the site's share of the amplitude, what the pair loop reads
   SF_DV,     // E(std.dev) + nugget  (diagonal / coincident value)
   SF_COUNT
 };

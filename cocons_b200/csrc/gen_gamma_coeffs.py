@@ -52,11 +52,30 @@ def of_t(f):
     return lambda t: f(mp.sqrt((t + 1) / 8))
 
 
+HIWORD_FROM = 6  # coefficients of t^6 and above (|c| < 1e-11, |t| <= 1) are rounded to doubles whose low 32 bits
+# are zero: ptxas encodes those as immediates of the DFMA instead of two UMOVs each, and the polynomial moves by
+# < 3e-18 (the functions are O(1))
+
+
+def hiword(v):
+    import struct
+    b = struct.unpack("<Q", struct.pack("<d", float(v)))[0]
+    b = (b + 0x80000000) & ~0xFFFFFFFF
+    return struct.unpack("<d", struct.pack("<Q", b))[0]
+
+
+def as_double(k, v):
+    return hiword(v) if k >= HIWORD_FROM else float(v)
+
+
 def emit(name, mono):
     print("// %s(mu) = sum_k c[k] t^k, t = 8 mu^2 - 1" % name)
     print("#define COCONS_%s_COEFFS { \\" % name.upper())
-    for v in mono:
-        print("  %s, \\" % mp.nstr(v, 20, min_fixed=0, max_fixed=0))
+    for k, v in enumerate(mono):
+        if k >= HIWORD_FROM:
+            print("  %s, \\" % hiword(v).hex())
+        else:
+            print("  %s, \\" % mp.nstr(v, 20, min_fixed=0, max_fixed=0))
     print("}")
 
 
@@ -70,8 +89,8 @@ if __name__ == "__main__":
             mu = mp.mpf(i) / 2000
             t = float(8 * mu * mu - 1)
             acc = 0.0
-            for v in reversed(mono):
-                acc = acc * t + float(v)
+            for k in range(9, -1, -1):  # bessel.cuh evaluates the terms up to t^9
+                acc = acc * t + as_double(k, mono[k])
             ref = f(mu)
             worst = max(worst, abs((mp.mpf(acc) - ref) / ref))
         print("// %s: last Chebyshev coeff %s, worst relative error of the double Horner form %s" % (
