@@ -38,60 +38,84 @@ constexpr double kTrapXHighNu = 18.0;   // for kHankelNuMax < nu <= kTrapNuMax t
 constexpr int kHankelTerms = 40;
 
 // exp(y) for -708 <= y < 709 (below: 0), the exponential of the hot loops (one call per node of the
-// trapezoidal rule below: ~17 per pair of the assembly kernel).  Table-driven: N = round(32 y / ln 2) = 32 n + j,
-// r = y - N ln2/32 (two-piece, |r| <= 0.0109), e^y = 2^n 2^(j/32) e^r with 2^(j/32) from a 32-entry table and
-// e^r = 1 + r + r^2 (1/2 + r/6 + r^2/24 + r^3/120 + r^4/720) (truncation 3e-18): 11 FP64 instructions, the
+// trapezoidal rule below: ~17 per pair of the assembly kernel).  Table-driven: N = round(128 y / ln 2) = 128 n + j,
+// r = y - N ln2/128 (two-piece, |r| <= 0.0027), e^y = 2^n 2^(j/128) e^r with 2^(j/128) from a 128-entry table and
+// e^r = 1 + r + r^2 (1/2 + r/6 + r^2/24 + r^3/120) (truncation 6e-19): 10 FP64 instructions, the
 // library routine (and a first version here with a degree-13 polynomial and no table) needs 19 plus two UMOVs
 // per 64-bit literal - ncu's source view of the assembly kernel: 11 % UMOV, 7 % LDCU.  The table is read with
-// ld.global.nc (256 B, two lines: lanes with different j do not serialise as they would on the constant
+// ld.global.nc (1 KB, L1-resident: lanes with different j do not serialise as they would on the constant
 // cache).  Worst error against long double on 25 000 arguments: 1.5 ulp (tests/test_host.py).
 #ifdef __CUDACC__
 __device__
 #endif
-    static const double kExp2Tab[32] = {
-        1.0, 1.0218971486541166782, 1.0442737824274138403, 1.0671404006768236182,
-        1.0905077326652576592, 1.1143867425958925363, 1.1387886347566916537, 1.1637248587775775138,
-        1.1892071150027210667, 1.2152473599804688781, 1.2418578120734840486, 1.2690509571917332226,
-        1.2968395546510096659, 1.3252366431597412946, 1.3542555469368927283, 1.3839098819638319549,
-        1.4142135623730950488, 1.44518080697704662, 1.4768261459394993114, 1.5091644275934227398,
-        1.5422108254079408236, 1.5759808451078864865, 1.6104903319492543082, 1.6457554781539648445,
-        1.6817928305074290861, 1.7186192981224779156, 1.7562521603732994831, 1.7947090750031071864,
-        1.8340080864093424635, 1.8741676341102999013, 1.9152065613971472939, 1.957144124175400269};
+    static const double kExp2Tab[128] = {
+        1, 1.0054299011128027264, 1.0108892860517004753, 1.0163783149109530957,
+        1.0218971486541166271, 1.0274459491187637461, 1.0330248790212284149, 1.0386341019613787306,
+        1.0442737824274137548, 1.0499440858006872102, 1.055645178360557157, 1.0613772272892620929,
+        1.0671404006768236972, 1.0729348675259755552, 1.0787607977571198603, 1.0846183622133092062,
+        1.0905077326652576897, 1.0964290818163768826, 1.1023825833078408909, 1.1083684117236787259,
+        1.1143867425958924322, 1.1204377524096067464, 1.1265216186082418481, 1.1326385195987191956,
+        1.1387886347566915646, 1.144972144431804173, 1.1511892299529826733, 1.1574400736337511209,
+        1.1637248587775774755, 1.1700437696832501899, 1.1763969916502812207, 1.1827847109843410145,
+        1.1892071150027210269, 1.1956643920398273284, 1.2021567314527030756, 1.2086843236265816248,
+        1.2152473599804689552, 1.221846032972757623, 1.2284805361068700247, 1.2351510639369334132,
+        1.241857812073484002, 1.2486009771892048192, 1.2553807570246910963, 1.2621973503942507389,
+        1.2690509571917332199, 1.2759417783963920012, 1.2828700160787782636, 1.2898358734066657227,
+        1.2968395546510096406, 1.3038812651919358121, 1.3109612115247644137, 1.3180796012660640493,
+        1.3252366431597413232, 1.3324325470831615004, 1.3396675240533029161, 1.3469417862329458035,
+        1.3542555469368926513, 1.3616090206382247541, 1.369002422974590516, 1.3764359707545301692,
+        1.3839098819638320226, 1.3914243757719262362, 1.3989796725383112364, 1.4065759938190154354,
+        1.4142135623730951455, 1.4218926021691655759, 1.4296133383919700233, 1.4373759974489823676,
+        1.4451808069770466503, 1.4530279958490526226, 1.4609177941806470447, 1.4688504333369818422,
+        1.4768261459394993462, 1.4848451658727523927, 1.492907728291264835, 1.5010140696264255844,
+        1.5091644275934228414, 1.5173590411982147419, 1.5255981507445384171, 1.533881997840955913,
+        1.5422108254079407441, 1.5505848776849999737, 1.5590044002378369292, 1.5674696399655529966,
+        1.5759808451078864966, 1.5845382652524937495, 1.5931421513422669989, 1.6017927556826934143,
+        1.6104903319492542835, 1.6192351351948637284, 1.628027421857347834, 1.6368674497669644108,
+        1.6457554781539649458, 1.6546917676561943011, 1.6636765803267363761, 1.6727101796415966284,
+        1.6817928305074290041, 1.6909247992693052787, 1.7001063537185234775, 1.7093377631004629258,
+        1.7186192981224779341, 1.7279512309618376698, 1.7373338352737062174, 1.7467673861991690476,
+        1.7562521603732994535, 1.7657884359332727264, 1.7753764925265211883, 1.7850166113189349648,
+        1.7947090750031071682, 1.8044541678066239321, 1.8142521755003988559, 1.8241033854070534126,
+        1.8340080864093424307, 1.8439665689586259845, 1.8539791250833854708, 1.8640460483977889794,
+        1.8741676341102999626, 1.884344179032334532, 1.8945759815869656073, 1.9048633418176741383,
+        1.9152065613971474001, 1.9256059436361250281, 1.9360617934922943473, 1.9465744175792332182,
+        1.9571441241754001794, 1.9677712232331758813, 1.9784560263879509279, 1.9891988469672663431};
 
 // Constants of the hot loops are chosen so that ptxas can encode them as 32-bit immediates (a double whose low
 // word is zero) wherever the arithmetic allows it - every other 64-bit literal costs two UMOV issue slots per
 // use, and the per-node body of the trapezoidal rule was 28 non-FP64 instructions against 19 FP64 ones:
-//   * 32 log2(e) only picks N, r is formed exactly whatever N is: 21 significant bits suffice;
-//   * ln2/32 = hi + lo with a 21-bit hi (fn hi is exact for |N| < 2^32) and a full-precision lo;
-//   * 1/120 and 1/720 multiply r^5 and r^6 (|r| <= 0.0109): rounding them to 21 bits moves e^r by < 1e-18.
+//   * 128 log2(e) only picks N, r is formed exactly whatever N is: 21 significant bits suffice;
+//   * ln2/128 = hi + lo with a 21-bit hi (fn hi is exact for |N| < 2^32) and a full-precision lo;
+//   * 1/120 multiplies r^5 (|r| <= 0.0027): rounding it to 21 bits moves e^r by < 1e-22.
 // ylo: a correction to the argument (|ylo| << 1) added after the reduction, where it is not lost to the rounding of y.
-template <bool kCheckUnderflow>
+template <bool kCheckUnderflow, bool kHasLow = false>
 COCONS_HD double exp_poly_impl(double y, double ylo = 0.0) {
   if (kCheckUnderflow && y < -708.0) return 0.0;
   const double kMagic = 6755399441055744.0;  // 2^52 + 2^51: the low word of 32 y log2(e) + kMagic is N
-  const double t = fma(y, 0x1.71547p+5, kMagic);
+  const double t = fma(y, 0x1.71547p+7, kMagic);
   const double fn = t - kMagic;
-  double r = fma(fn, -0x1.62e42p-6, y);          // exact
-  r = fma(fn, -0x1.fdf473de6af28p-27, r) + ylo;
-  double q = fma(r, 0x1.6c16cp-10, 0x1.11111p-7);
-  q = fma(q, r, 1.0 / 24.0);
+  double r = fma(fn, -0x1.62e42p-8, y);          // exact
+  r = fma(fn, -0x1.fdf473de6af28p-29, r);
+  if (kHasLow) r += ylo;  // (not folded away for ylo = 0: r + 0.0 is not r for r = -0.0)
+  double q = fma(r, 0x1.11111p-7, 1.0 / 24.0);
   q = fma(q, r, 1.0 / 6.0);
   q = fma(q, r, 0.5);
   const double p = fma(q * r, r, r);  // e^r - 1
 #ifdef __CUDA_ARCH__
   const int N = __double2loint(t);
-  const double T = __ldg(&kExp2Tab[N & 31]);
+  const double T = __ldg(&kExp2Tab[N & 127]);
   const double e = fma(T, p, T);
-  return __hiloint2double(__double2hiint(e) + ((N >> 5) << 20), __double2loint(e));
+  return __hiloint2double(__double2hiint(e) + ((N >> 7) << 20), __double2loint(e));
 #else
   const long long N = (long long)fn;
-  const double T = kExp2Tab[N & 31];
-  return ldexp(fma(T, p, T), (int)(N >> 5));
+  const double T = kExp2Tab[N & 127];
+  return ldexp(fma(T, p, T), (int)(N >> 7));
 #endif
 }
 
 COCONS_HD double exp_poly(double y) { return exp_poly_impl<true>(y); }
-COCONS_HD double exp_poly2(double y, double ylo) { return exp_poly_impl<true>(y, ylo); }
+COCONS_HD double exp_poly2(double y, double ylo) { return exp_poly_impl<true, true>(y, ylo); }
 // for arguments known to stay above -708 (the nodes of the trapezoidal rule: the loop leaves long before)
 COCONS_HD double exp_poly_nocheck(double y) { return exp_poly_impl<false>(y); }
 
@@ -291,7 +315,7 @@ COCONS_HD void bessel_k_cf2_scaled(double mu, double x, double& kmu, double& kmu
 // (C_{k+1} = C_k + D_{k+1}, D_{k+1} = D_k + 4 sinh^2(nu h / 2) C_k).  Worst error against 40-digit mpmath
 // on a 41 x 24 grid of (x, nu <= 6): 1.0e-15 (Steed's CF2 above: 2.9e-15) at about a third of CF2's
 // instructions - CF2 needs a division per step and ~40 steps at x = 2.
-// Generated by: mpmath, 50 digits, cosh(k * 5/32) - 1, k = 0..31.
+// Generated by: mpmath, 50 digits, (cosh(k * 5/32) - 1) * 128 / ln 2, k = 0..31 (the unit of exp_node below).
 constexpr double kTrapH = 0.15625;
 constexpr double kTrapNuMax = 6.0;
 constexpr int kTrapNodes = 32;
@@ -301,14 +325,41 @@ __constant__
 static const
 #endif
     double kTrapC[kTrapNodes] = {
-        0.0, 0.012231886738463469997, 0.049226785060219076999, 0.11188972977761219479,
-        0.20175369297560632423, 0.32101708629361609274, 0.47259754236986293334, 0.6602032911453254225,
-        0.88842387716101573823, 1.1628424371359932486, 1.4901722845593502931, 1.878421142670688936,
-        2.3370870435875205143, 2.8773906860114650123, 3.5125499358595403409, 4.2581031851418046566,
-        5.1322894796636861166, 6.1564947149110021668, 7.3557748157527258146, 8.7594686989112350851,
-        10.4019160135750677, 12.323297218797946605, 14.570616549147269181, 17.198851915651020399,
-        20.272299872959396082, 23.866148555693112154, 28.06831706393691852, 32.981606296188367655,
-        38.726213847251883289, 45.442674494970527276, 53.295298211196782517, 62.476189803723952335};
+        0.0, 2.25880093930198081271, 9.09046255171647670791, 20.662113059400613363,
+        37.2568386991285421201, 59.2806090798623185295, 87.2722087313040666854, 121.916417806583484605,
+        164.060764388805504502, 214.736258226090705961, 275.182613120505841295, 346.878575005693816417,
+        431.578097652424257722, 531.353250996330622076, 648.64491178744388428, 786.322476646090392466,
+        947.754058331826991611, 1136.88888249103556949, 1358.35390061854541354, 1617.56698275089144305,
+        1920.86945901161542931, 2275.68125247495073464, 2690.6823984831265807, 3176.02539106475206419,
+        3743.58355124895790321, 4407.24149330147192419, 5183.23479478283033573, 6090.54718004008576447,
+        7151.37493373898197335, 8391.669905744046004, 9841.7743912949811834, 11537.1634180441812647};
+
+// e^{z ln2/128}, z = a c, for the nodes of the rule: the node constants c carry the factor 128/ln2, so N = round(z)
+// and the reduced argument f = a c - N is ONE fma of the exact product (no two-piece reduction, and the product is
+// never rounded); e^{f ln2/128} - 1 = f (a1 + f (a2 + f (a3 + f (a4 + f a5)))), a_i = (ln2/128)^i / i!, |f| <= 1/2
+// (truncation 6e-19; a4, a5 as 21-bit immediates).  No underflow test: the loop leaves long before
+// (z > -60 * 185).  9 FP64 instructions.
+COCONS_HD double exp_node(double a, double c) {
+  const double kMagic = 6755399441055744.0;
+  const double t = fma(a, c, kMagic);
+  const double fn = t - kMagic;
+  const double f = fma(a, c, -fn);
+  double q = fma(f, 0x1.5d88000000000p-45, 0x1.3b2ab00000000p-35);
+  q = fma(q, f, 0x1.c6b08d704a0c0p-26);
+  q = fma(q, f, 0x1.ebfbdff82c58fp-17);
+  q = fma(q, f, 0x1.62e42fefa39efp-8);
+  const double p = q * f;
+#ifdef __CUDA_ARCH__
+  const int N = __double2loint(t);
+  const double T = __ldg(&kExp2Tab[N & 127]);
+  const double e = fma(T, p, T);
+  return __hiloint2double(__double2hiint(e) + ((N >> 7) << 20), __double2loint(e));
+#else
+  const long long N = (long long)fn;
+  const double T = kExp2Tab[N & 127];
+  return ldexp(fma(T, p, T), (int)(N >> 7));
+#endif
+}
 
 COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
   // sinh(a), a = nu h / 2 <= 0.47: odd series to a^15 (next term 2e-18 relative)
@@ -334,12 +385,12 @@ COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
 #pragma unroll
 #endif
   for (int k = 1; k < kTrapNodes - 1; k += 2) {
-    const double t1 = exp_poly_nocheck(nx * kTrapC[k]) * C;
+    const double t1 = exp_node(nx, kTrapC[k]) * C;
     D = fma(delta, C, D);
     C += D;
-    const double t2 = exp_poly_nocheck(nx * kTrapC[k + 1]) * C;
+    const double t2 = exp_node(nx, kTrapC[k + 1]) * C;
     sum += t1 + t2;
-    if (t2 < 1e-17 * sum) break;
+    if (t2 < 5e-18) break;  // sum >= 1/2: below 1e-17 of it
     D = fma(delta, C, D);
     C += D;
   }
