@@ -112,7 +112,7 @@ constexpr double kTinyCorr = 1e-250;
 
 template <int MODE, class SlowAmp>
 __device__ __forceinline__ double pair_cov(const SiteA& a, const SiteB& b, double global_range, double nu_fixed,
-                                           bool& coincident, SlowAmp slow_amp) {
+                                           bool& coincident, SlowAmp slow_amp, const double* exp_tab = nullptr) {
   // sigma11, sigma22, sigma12 of the averaged kernel matrix (:260-268)
   const double s11 = __dmul_rn(__dadd_rn(a.r, b.r), 0.5);
   const double s22 = __dmul_rn(__dadd_rn(__fma_rn(a.r, a.a2, b.p22), b.e22), 0.5);
@@ -147,7 +147,7 @@ __device__ __forceinline__ double pair_cov(const SiteA& a, const SiteB& b, doubl
   } else if (MODE == SM_FIVEHALF) {
     corr = __dmul_rn(__dadd_rn(__dadd_rn(1.0, Q), __ddiv_rn(__dmul_rn(Q, Q), 3.0)), exp(-Q));  // :242
   } else {
-    corr = (Q < 706.0) ? matern_corr(nu, Q) : matern_corr_tail(nu, Q);  // :291-305
+    corr = (Q < 706.0) ? matern_corr(nu, Q, exp_tab) : matern_corr_tail(nu, Q);  // :291-305
   }
   // corr * sigma_i * sigma_j * sqrt(D_i sin t_i D_j sin t_j) / sqrt(det) (:295-297) with the per-site parts hoisted
   if (!(fabs(corr) >= kTinyCorr)) return slow_amp(corr, det);
@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
   // slab == 1: C holds only the tile columns [col_tile0, col_tile0 + gridDim.y) (a column panel of a
   //            distributed matrix); blockIdx.x runs over the tile rows from col_tile0 down.
   __shared__ double cs[9][kAsmTile];
+  __shared__ double etab[kAsmTile];  // 2^(j/128) of the node exponential (bessel.cuh)
   __shared__ int corig[kAsmTile];
+  static_assert(kAsmTile == 128, "one table entry per thread");
   int tr, tc;
   if (slab >= 2) {
     // slab = 2 + 16 (world + 64 rank): C holds ALL column panels of one rank of the block-cyclic layout (csrc/dist.cu:
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
     cs[7][tid] = ok ? T.f(SF_AMP)[J] : 0.0;
     cs[8][tid] = ok ? T.f(SF_DV)[J] : 1.0;
     corig[tid] = (ok && T.orig) ? T.orig[J] : (int)J;
+    etab[tid] = kExp2Tab[tid];
   }
   SiteB b;
   double dvI = 1.0;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(kAsmTile, COCONS_ASM_MINBLOCKS) assemble_lower
       bool coincident;
       v = pair_cov<MODE>(a, b, global_range, nu_fixed, coincident, [&](double corr, double det) {
         return amp_reference_order(corr, det, T.f(SF_SIG)[J], T.f(SF_SIG)[I], T.f(SF_W)[J], T.f(SF_W)[I]);
-      });
+      }, etab);
       // :284-286 - the value of the lower caller-order index of the pair
       if (coincident) v = (corig[j] < origI) ? a.dv : dvI;
     }

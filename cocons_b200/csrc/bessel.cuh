@@ -339,7 +339,9 @@ static const
 // never rounded); e^{f ln2/128} - 1 = f (a1 + f (a2 + f (a3 + f (a4 + f a5)))), a_i = (ln2/128)^i / i!, |f| <= 1/2
 // (truncation 6e-19; a4, a5 as 21-bit immediates).  No underflow test: the loop leaves long before
 // (z > -60 * 185).  9 FP64 instructions.
-COCONS_HD double exp_node(double a, double c) {
+// tab: the 2^(j/128) table; the assembly kernel passes a copy in shared memory (a 32-bit address: two integer
+// instructions fewer per node than the 64-bit global one), everyone else the global table.
+COCONS_HD double exp_node(double a, double c, const double* tab) {
   const double kMagic = 6755399441055744.0;
   const double t = fma(a, c, kMagic);
   const double fn = t - kMagic;
@@ -351,7 +353,7 @@ COCONS_HD double exp_node(double a, double c) {
   const double p = q * f;
 #ifdef __CUDA_ARCH__
   const int N = __double2loint(t);
-  const double T = __ldg(&kExp2Tab[N & 127]);
+  const double T = tab ? tab[N & 127] : __ldg(&kExp2Tab[N & 127]);
   const double e = fma(T, p, T);
   return __hiloint2double(__double2hiint(e) + ((N >> 7) << 20), __double2loint(e));
 #else
@@ -361,7 +363,7 @@ COCONS_HD double exp_node(double a, double c) {
 #endif
 }
 
-COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
+COCONS_HD double bessel_k_trap_scaled(double nu, double x, const double* tab = nullptr) {
   // sinh(a), a = nu h / 2 <= 0.47: odd series to a^15 (next term 2e-18 relative)
   const double a = 0.5 * kTrapH * nu, a2 = a * a;
   // (the three highest coefficients rounded to 21 bits - immediates, see exp_poly - move sinh by < 2e-17 relative)
@@ -385,10 +387,10 @@ COCONS_HD double bessel_k_trap_scaled(double nu, double x) {
 #pragma unroll
 #endif
   for (int k = 1; k < kTrapNodes - 1; k += 2) {
-    const double t1 = exp_node(nx, kTrapC[k]) * C;
+    const double t1 = exp_node(nx, kTrapC[k], tab) * C;
     D = fma(delta, C, D);
     C += D;
-    const double t2 = exp_node(nx, kTrapC[k + 1]) * C;
+    const double t2 = exp_node(nx, kTrapC[k + 1], tab) * C;
     sum += t1 + t2;
     if (t2 < 5e-18) break;  // sum >= 1/2: below 1e-17 of it
     D = fma(delta, C, D);
@@ -486,7 +488,7 @@ COCONS_HD double bessel_k(double nu, double x) {
 
 // Matern correlation factor  2^{1-nu}/Gamma(nu) * Q^nu * K_nu(Q)   (eps < Q < 706),
 // the quantity formed at src/cocons_full.cpp:293-294.
-COCONS_HD double matern_corr(double nu, double Q) {
+COCONS_HD double matern_corr(double nu, double Q, const double* exp_tab = nullptr) {
   const int nl = (int)(nu + 0.5);
   const double mu = nu - (double)nl;
   const TemmeGammas G = temme_gammas(mu);
@@ -512,7 +514,7 @@ COCONS_HD double matern_corr(double nu, double Q) {
   if (band == 2) {
     ks = bessel_k_hankel_scaled(nu, Q);
   } else if (band == 3) {
-    ks = bessel_k_trap_scaled(nu, Q);
+    ks = bessel_k_trap_scaled(nu, Q, exp_tab);
   } else {
     double kmu, kmu1;
     bessel_k_cf2_scaled(mu, Q, kmu, kmu1);
