@@ -1,0 +1,133 @@
+// TEST SCAFFOLDING - host-emulated runs of the shipped assembly kernels (see cuda_runtime.h in this directory).
+// ASSEMBLY_INC / TAPER_INC are cocons_b200/csrc/assembly.cu and taper.cu with their <<<...>>> launches rewritten
+// by tests/host_emul/build.py; everything else in them is compiled as it ships.  The functions below repeat
+// the few lines of orchestration the library's entry points put around those launches:
+//   emu_cov_square    cov_square()            cocons_b200/csrc/capi.cu  (cocons_cov_rns / cocons_cov_rns_classic)
+//   emu_cov_pred      cocons_cov_rns_pred()   capi.cu
+//   emu_ctx_lower     assemble_and_factor()   capi.cu  (Morton-ordered, padded, lower triangle only)
+//   emu_dist_slabs    cocons_dist_assemble()  cocons_b200/csrc/dist.cu (one rank's column panels, both launch modes)
+//   emu_taper_*       taper_entries_host() / the TS_LOWER sink of assemble_and_factor(taper = true)
+#include "cuda_runtime.h"  // the emulation shim (found first through -I tests/host_emul)
+
+#include ASSEMBLY_INC
+#include TAPER_INC
+
+namespace cocons {
+void set_error(const char*, ...) {}
+void note_launch(int) {}
+}  // namespace cocons
+
+using namespace cocons;
+
+extern "C" {
+
+long emu_launches() { return emul::launches; }
+long emu_barrier_launches() { return emul::barrier_launches; }
+
+int emu_cov_square(int par, int64_t n, int64_t p, const double* locs, const double* X, const double* theta6,
+                   const double* limits, double* out) {
+  const double lim[2] = {limits ? limits[0] : 0.0, limits ? limits[1] : 0.0};
+  double nu_fixed;
+  const int mode = smooth_mode_for(par, (int)p, theta6, lim, &nu_fixed);
+  const double global_range = 1 / std::exp(-2 * theta6[p]);
+  std::vector<double> S((size_t)SF_COUNT * n);
+  SiteTable T{S.data(), n, nullptr};
+  launch_site_stage(n, n, (int)p, X, n, locs, n, theta6, lim[0], lim[1], mode, T, nullptr);
+  launch_assemble_lower(n, n, T, global_range, nu_fixed, mode, out, n, nullptr);
+  launch_symmetrize(n, out, n, nullptr);
+  return mode;
+}
+
+int emu_cov_pred(int64_t n, int64_t m, int64_t p, const double* locs, const double* locs_pred, const double* X,
+                 const double* X_pred, const double* theta6, const double* limits, double* out) {
+  const double global_range = 1 / std::exp(-2 * theta6[p]);
+  std::vector<double> S((size_t)SF_COUNT * n), Sp((size_t)SF_COUNT * m);
+  SiteTable T{S.data(), n, nullptr}, P{Sp.data(), m, nullptr};
+  launch_site_stage(n, n, (int)p, X, n, locs, n, theta6, limits[0], limits[1], SM_GENERAL, T, nullptr);
+  launch_site_stage(m, m, (int)p, X_pred, m, locs_pred, m, theta6, limits[0], limits[1], SM_GENERAL, P, nullptr);
+  launch_assemble_cross(m, n, P, T, global_range, out, m, nullptr);
+  return 0;
+}
+
+void emu_morton(int64_t n, const double* locs, int64_t* perm) { morton_order(n, locs, perm); }
+
+// the context's matrix: sites already in the context's order (locs / X with leading dimension n_pad, orig = the
+// caller index of each), n_pad x n_pad output of which only the lower triangle (and whole diagonal tiles) is written
+int emu_ctx_lower(int par, int64_t n, int64_t n_pad, int64_t p, const double* locs, const double* X,
+                  const double* theta6, const double* limits, const int* orig, double* A) {
+  const double lim[2] = {limits ? limits[0] : 0.0, limits ? limits[1] : 0.0};
+  double nu_fixed;
+  const int mode = smooth_mode_for(par, (int)p, theta6, lim, &nu_fixed);
+  const double global_range = 1 / std::exp(-2 * theta6[p]);
+  std::vector<double> S((size_t)SF_COUNT * n_pad);
+  SiteTable T{S.data(), n_pad, orig};
+  launch_site_stage(n, n_pad, (int)p, X, n_pad, locs, n_pad, theta6, lim[0], lim[1], mode, T, nullptr);
+  launch_assemble_lower(n, n_pad, T, global_range, nu_fixed, mode, A, n_pad, nullptr);
+  return mode;
+}
+
+// one rank's slab of the block-cyclic layout (512-wide column panels dealt in a snake; csrc/dist.cu):
+// cyclic = 1: every local panel in ONE launch (launch_assemble_cyclic), 0: a launch per panel (launch_assemble_panel)
+int emu_dist_slabs(int par, int64_t n, int64_t n_pad, int64_t p, const double* locs, const double* X,
+                   const double* theta6, const double* limits, const int* orig, int world, int rank, int64_t nlocal,
+                   int cyclic, double* slab) {
+  const double lim[2] = {limits ? limits[0] : 0.0, limits ? limits[1] : 0.0};
+  double nu_fixed;
+  const int mode = smooth_mode_for(par, (int)p, theta6, lim, &nu_fixed);
+  const double global_range = 1 / std::exp(-2 * theta6[p]);
+  std::vector<double> S((size_t)SF_COUNT * n_pad);
+  SiteTable T{S.data(), n_pad, orig};
+  launch_site_stage(n, n_pad, (int)p, X, n_pad, locs, n_pad, theta6, lim[0], lim[1], mode, T, nullptr);
+  const int64_t kPanelW = 512, npanels = (n_pad + kPanelW - 1) / kPanelW;
+  if (cyclic) {
+    launch_assemble_cyclic(n, n_pad, T, global_range, nu_fixed, mode, slab, n_pad, world, rank, nlocal, nullptr);
+  } else {
+    for (int64_t lp = 0; lp < nlocal; ++lp) {
+      const int64_t K = lp * world + ((lp & 1) ? world - 1 - rank : rank);
+      if (K >= npanels) continue;
+      const int64_t width = std::min<int64_t>(kPanelW, n_pad - K * kPanelW);
+      launch_assemble_panel(n, n_pad, T, global_range, nu_fixed, mode, slab + lp * kPanelW * n_pad, n_pad,
+                            (int)(K * 4), (int)(width / 128), nullptr);
+    }
+  }
+  return mode;
+}
+
+// entry vectors of cov_rns_taper (m == 0) / cov_rns_taper_pred (m > 0)
+int emu_taper_entries(int64_t n, int64_t m, int64_t p, const double* locs, const double* locs_rows, const double* X,
+                      const double* X_rows, const double* theta6, const double* limits, const int* colindices,
+                      const int* rowpointers, int64_t nnz, double* out) {
+  const bool square = (m == 0);
+  const int64_t nrows = square ? n : m;
+  double nu_fixed = 0.0;
+  const int mode = square ? smooth_mode_for(COCONS_PAR_DIFF, (int)p, theta6, limits, &nu_fixed) : (int)SM_GENERAL;
+  std::vector<double> S((size_t)TF_COUNT * n), Sr((size_t)TF_COUNT * std::max<int64_t>(m, 1));
+  TaperTable C{S.data(), n}, R{S.data(), n};
+  launch_taper_site_stage(n, (int)p, X, n, locs, n, theta6, limits[0], limits[1], mode, 0, C, nullptr);
+  if (!square) {
+    R = TaperTable{Sr.data(), m};
+    launch_taper_site_stage(m, (int)p, X_rows, m, locs_rows, m, theta6, limits[0], limits[1], mode, 1, R, nullptr);
+  }
+  launch_taper_entries(0, nnz, nrows, colindices, rowpointers, R, C, square ? 1 : 0, mode, nu_fixed,
+                       TaperSink{TS_VECTOR, out, nullptr, nullptr, nullptr, 0, 0}, nullptr);
+  return mode;
+}
+
+// the dense sink of the tapered objective: A (n_pad x n_pad, zeroed by the caller) receives taper[e] * cov[e] on the
+// pattern's lower triangle in the context's ordering (inv: caller index -> position), unit diagonal in the padding
+int emu_taper_lower(int64_t n, int64_t n_pad, int64_t p, const double* locs_sorted, const double* X_sorted,
+                    const double* theta6, const double* limits, const int* colindices, const int* rowpointers,
+                    int64_t nnz, const double* taper, const int* inv, double* A) {
+  double nu_fixed = 0.0;
+  const int mode = smooth_mode_for(COCONS_PAR_DIFF, (int)p, theta6, limits, &nu_fixed);
+  std::vector<double> S((size_t)TF_COUNT * n_pad);
+  TaperTable T{S.data(), n_pad};
+  launch_taper_site_stage(n, (int)p, X_sorted, n_pad, locs_sorted, n_pad, theta6, limits[0], limits[1], mode, 0, T,
+                          nullptr);
+  launch_taper_pad_diag(n, n_pad, A, n_pad, nullptr);
+  launch_taper_entries(0, nnz, n, colindices, rowpointers, T, T, 1, mode, nu_fixed,
+                       TaperSink{TS_LOWER, nullptr, taper, inv, A, n_pad, 0}, nullptr);
+  return mode;
+}
+
+}  // extern "C"
