@@ -56,6 +56,7 @@ SIGNATURES = {
     "cocons_ctx_get_factor": (ctypes.c_int, [_vp, _dp, _lp]),
     "cocons_ctx_factor_rows": (ctypes.c_int, [_vp, _lp, _i64, _dp, _lp]),
     "cocons_debug_solve_units": (ctypes.c_int64, [_i64, _i32p, _i64]),
+    "cocons_ctx_dims": (ctypes.c_int, [_vp, _vp]),
     "cocons_ctx_timings": (ctypes.c_int, [_vp, _dp]),
     "cocons_ctx_debug_checksums": (ctypes.c_int, [_vp, _dp]),
     "cocons_ctx_kernel_timing": (ctypes.c_int, [_vp, _dp, _dp]),

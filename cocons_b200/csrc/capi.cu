@@ -1272,6 +1272,12 @@ int64_t cocons_debug_solve_units(int64_t n_pad, int32_t* units4, int64_t capacit
   return count;
 }
 
+int cocons_ctx_dims(cocons_ctx* c, int64_t* dims4) {
+  if (!c || !dims4) return COCONS_ERR_ARG;
+  dims4[0] = c->n, dims4[1] = c->p, dims4[2] = c->r, dims4[3] = c->q;
+  return 0;
+}
+
 int cocons_ctx_timings(cocons_ctx* c, double* ms4) {
   if (!c || !ms4) return COCONS_ERR_ARG;
   for (int i = 0; i < 4; ++i) ms4[i] = c->ms[i];

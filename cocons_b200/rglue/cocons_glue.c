@@ -40,21 +40,34 @@ static SEXP list_get(SEXP list, const char* name) {
   Rf_error("Index out of bounds: [index='%s'].", name);
 }
 
-/* named list -> 6 x p block (malloc'd; caller frees), all aspects must have length p */
+/* named list -> 6 x p block (malloc'd; caller frees), all aspects must have length p.  Every check that can raise
+ * an R error runs BEFORE the buffer exists: Rf_error() does not return, so nothing may be owned when it is called */
 static double* pack_theta(SEXP theta, int p) {
-  double* out = (double*)malloc(sizeof(double) * 6 * (size_t)p);
-  if (!out) Rf_error("out of memory");
+  SEXP part[6];
   for (int a = 0; a < 6; ++a) {
-    SEXP v = PROTECT(as_real(list_get(theta, kAspects[a])));
-    if (LENGTH(v) != p) {
-      free(out);
-      UNPROTECT(1);
-      Rf_error("theta$%s has length %d, expected %d", kAspects[a], LENGTH(v), p);
-    }
-    memcpy(out + (size_t)a * p, REAL(v), sizeof(double) * (size_t)p);
-    UNPROTECT(1);
+    part[a] = PROTECT(as_real(list_get(theta, kAspects[a])));
+    if (LENGTH(part[a]) != p) Rf_error("theta$%s has length %d, expected %d", kAspects[a], LENGTH(part[a]), p);
   }
+  double* out = (double*)malloc(sizeof(double) * 6 * (size_t)(p > 0 ? p : 1));
+  if (!out) Rf_error("out of memory");
+  for (int a = 0; a < 6; ++a) memcpy(out + (size_t)a * p, REAL(part[a]), sizeof(double) * (size_t)p);
+  UNPROTECT(6);
   return out;
+}
+
+/* shape checks the reference leaves to Rcpp's bounds-unchecked operator(): here a mismatch would make the device
+ * read past a host buffer, so it is an R error instead */
+static void need(int ok, const char* who, const char* what) {
+  if (!ok) Rf_error("%s: %s", who, what);
+}
+static int rows_of(SEXP x) { return Rf_isMatrix(x) ? Rf_nrows(x) : LENGTH(x); }
+static void check_sites(const char* who, SEXP locs, SEXP x) {
+  need(Rf_isMatrix(locs) && Rf_ncols(locs) == 2, who, "locs must be a matrix with two columns");
+  need(Rf_isMatrix(x) && Rf_nrows(x) == Rf_nrows(locs), who, "x_covariates must be a matrix with nrow(locs) rows");
+  need(Rf_nrows(locs) >= 1 && Rf_ncols(x) >= 1, who, "empty design");
+}
+static void check_limits(const char* who, SEXP lim) {
+  need(LENGTH(lim) == 2, who, "smooth_limits must have two elements");
 }
 
 static void raise(int status) {
@@ -72,6 +85,8 @@ SEXP _cocons_sumsmoothlone(SEXP xS, SEXP lambdaS, SEXP alphaS) {
 
 SEXP _cocons_cov_rns(SEXP thetaS, SEXP locsS, SEXP xS, SEXP limS) {
   SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS)), lim = PROTECT(as_real(limS));
+  check_sites("cov_rns", locs, x);
+  check_limits("cov_rns", lim);
   const int n = Rf_nrows(locs), p = Rf_ncols(x);
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
@@ -85,6 +100,10 @@ SEXP _cocons_cov_rns(SEXP thetaS, SEXP locsS, SEXP xS, SEXP limS) {
 SEXP _cocons_cov_rns_pred(SEXP thetaS, SEXP locsS, SEXP locsPredS, SEXP xS, SEXP xPredS, SEXP limS) {
   SEXP locs = PROTECT(as_real(locsS)), lp = PROTECT(as_real(locsPredS));
   SEXP x = PROTECT(as_real(xS)), xp = PROTECT(as_real(xPredS)), lim = PROTECT(as_real(limS));
+  check_sites("cov_rns_pred", locs, x);
+  check_sites("cov_rns_pred", lp, xp);
+  need(Rf_ncols(xp) == Rf_ncols(x), "cov_rns_pred", "x_covariates_pred and x_covariates differ in columns");
+  check_limits("cov_rns_pred", lim);
   const int n = Rf_nrows(locs), m = Rf_nrows(lp), p = Rf_ncols(x);
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, n));
@@ -97,6 +116,7 @@ SEXP _cocons_cov_rns_pred(SEXP thetaS, SEXP locsS, SEXP locsPredS, SEXP xS, SEXP
 
 SEXP _cocons_cov_rns_classic(SEXP thetaS, SEXP locsS, SEXP xS) {
   SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS));
+  check_sites("cov_rns_classic", locs, x);
   const int n = Rf_nrows(locs), p = Rf_ncols(x);
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
@@ -116,16 +136,18 @@ SEXP _cocons_cov_rns_taper_pred(SEXP thetaS, SEXP locsS, SEXP locsPredS, SEXP xS
   SEXP locs = PROTECT(as_real(locsS)), lp = PROTECT(as_real(locsPredS));
   SEXP x = PROTECT(as_real(xS)), xp = PROTECT(as_real(xPredS)), lim = PROTECT(as_real(limS));
   SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS));
+  check_sites("cov_rns_taper_pred", locs, x);
+  check_sites("cov_rns_taper_pred", lp, xp);
+  need(Rf_ncols(xp) == Rf_ncols(x), "cov_rns_taper_pred", "x_covariates_pred and x_covariates differ in columns");
+  check_limits("cov_rns_taper_pred", lim);
   const int n = Rf_nrows(locs), m = Rf_nrows(lp), p = Rf_ncols(x);
+  need(LENGTH(row) == m + 1, "cov_rns_taper_pred", "rowpointers must have nrow(locs_pred) + 1 elements");
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(col)));
-  int rc = (LENGTH(row) == m + 1)
-               ? cocons_cov_rns_taper_pred(n, m, p, REAL(locs), REAL(lp), REAL(x), REAL(xp), th, REAL(lim),
-                                           INTEGER(col), INTEGER(row), XLENGTH(col), REAL(out))
-               : -100;
+  int rc = cocons_cov_rns_taper_pred(n, m, p, REAL(locs), REAL(lp), REAL(x), REAL(xp), th, REAL(lim), INTEGER(col),
+                                     INTEGER(row), XLENGTH(col), REAL(out));
   free(th);
   UNPROTECT(8);
-  if (rc == -100) Rf_error("cov_rns_taper_pred: rowpointers must have nrow(locs_pred) + 1 elements");
   raise(rc);
   return out;
 }
@@ -133,15 +155,16 @@ SEXP _cocons_cov_rns_taper_pred(SEXP thetaS, SEXP locsS, SEXP locsPredS, SEXP xS
 SEXP _cocons_cov_rns_taper(SEXP thetaS, SEXP locsS, SEXP xS, SEXP colS, SEXP rowS, SEXP limS) {
   SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS)), lim = PROTECT(as_real(limS));
   SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS));
+  check_sites("cov_rns_taper", locs, x);
+  check_limits("cov_rns_taper", lim);
   const int n = Rf_nrows(locs), p = Rf_ncols(x);
+  need(LENGTH(row) == n + 1, "cov_rns_taper", "rowpointers must have nrow(locs) + 1 elements");
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(col)));
-  int rc = (LENGTH(row) == n + 1) ? cocons_cov_rns_taper(n, p, REAL(locs), REAL(x), th, REAL(lim), INTEGER(col),
-                                                         INTEGER(row), XLENGTH(col), REAL(out))
-                                  : -100;
+  int rc = cocons_cov_rns_taper(n, p, REAL(locs), REAL(x), th, REAL(lim), INTEGER(col), INTEGER(row), XLENGTH(col),
+                                REAL(out));
   free(th);
   UNPROTECT(6);
-  if (rc == -100) Rf_error("cov_rns_taper: rowpointers must have nrow(locs) + 1 elements");
   raise(rc);
   return out;
 }
@@ -153,9 +176,13 @@ SEXP _cocons_n2ll_dense(SEXP kindS, SEXP thetaS, SEXP locsS, SEXP xS, SEXP limS,
   SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS)), lim = PROTECT(as_real(limS));
   SEXP z = PROTECT(as_real(zS)), mean = PROTECT(as_real(meanS));
   SEXP xb = PROTECT(Rf_isNull(xbS) ? xbS : as_real(xbS));
+  check_sites("n2ll_dense", locs, x);
+  check_limits("n2ll_dense", lim);
   const int n = Rf_nrows(locs), p = Rf_ncols(x);
   const int r = Rf_isMatrix(z) ? Rf_ncols(z) : 1;
   const int q = Rf_isNull(xb) ? 0 : (Rf_isMatrix(xb) ? Rf_ncols(xb) : 1);
+  need(rows_of(z) == n, "n2ll_dense", "z must have nrow(locs) rows");
+  need(q == 0 || rows_of(xb) == n, "n2ll_dense", "x_betas must have nrow(locs) rows");
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, 4 + r));
   double logdet = R_NaReal, ldw = 0.0;
@@ -173,12 +200,14 @@ SEXP _cocons_n2ll_dense(SEXP kindS, SEXP thetaS, SEXP locsS, SEXP xS, SEXP limS,
 /* ---- device-resident context behind an external pointer --------------------------------- */
 
 static void ctx_finalizer(SEXP ptr) {
+  if (TYPEOF(ptr) != EXTPTRSXP) return;
   cocons_ctx* c = (cocons_ctx*)R_ExternalPtrAddr(ptr);
   if (c) cocons_ctx_destroy(c);
   R_ClearExternalPtr(ptr);
 }
 
 static cocons_ctx* ctx_of(SEXP ptr) {
+  if (TYPEOF(ptr) != EXTPTRSXP) Rf_error("cocons_b200: not a context (external pointer expected)");
   cocons_ctx* c = (cocons_ctx*)R_ExternalPtrAddr(ptr);
   if (!c) Rf_error("cocons_b200: the context has been released");
   return c;
@@ -186,6 +215,8 @@ static cocons_ctx* ctx_of(SEXP ptr) {
 
 SEXP _cocons_ctx_new(SEXP locsS, SEXP xS, SEXP zS, SEXP deviceS) {
   SEXP locs = PROTECT(as_real(locsS)), x = PROTECT(as_real(xS)), z = PROTECT(as_real(zS));
+  check_sites("ctx_new", locs, x);
+  need(rows_of(z) == Rf_nrows(locs), "ctx_new", "z must have nrow(locs) rows");
   const int n = Rf_nrows(locs), p = Rf_ncols(x), r = Rf_isMatrix(z) ? Rf_ncols(z) : 1;
   cocons_ctx* c = NULL;
   int rc = cocons_ctx_create(Rf_asInteger(deviceS), n, p, r, REAL(locs), REAL(x), REAL(z), NULL, &c);
@@ -202,17 +233,44 @@ SEXP _cocons_ctx_free(SEXP ptr) {
   return R_NilValue;
 }
 
+/* {n, p, r, q} of a live context */
+typedef struct {
+  cocons_ctx* c;
+  int n, p, r, q;
+} ctx_view;
+
+static ctx_view view_of(SEXP ptr) {
+  ctx_view v;
+  int64_t d[4] = {0, 0, 0, 0};
+  v.c = ctx_of(ptr);
+  if (cocons_ctx_dims(v.c, d) != 0) Rf_error("cocons_b200: %s", cocons_last_error());
+  v.n = (int)d[0], v.p = (int)d[1], v.r = (int)d[2], v.q = (int)d[3];
+  return v;
+}
+
+/* prediction sites against a context: m x 2 coordinates, m x p design */
+static int check_pred_sites(const char* who, const ctx_view* v, SEXP lp, SEXP xp) {
+  need(Rf_isMatrix(lp) && Rf_ncols(lp) == 2, who, "locs_pred must be a matrix with two columns");
+  need(Rf_isMatrix(xp) && Rf_nrows(xp) == Rf_nrows(lp) && Rf_ncols(xp) == v->p, who,
+       "x_covariates_pred must be nrow(locs_pred) x p");
+  return Rf_nrows(lp);
+}
+
 SEXP _cocons_ctx_set_z(SEXP ptr, SEXP zS) {
+  const ctx_view v = view_of(ptr);
   SEXP z = PROTECT(as_real(zS));
-  int rc = cocons_ctx_set_z(ctx_of(ptr), REAL(z));
+  need(XLENGTH(z) == (R_xlen_t)v.n * v.r, "ctx_set_z", "z must be n x r like the z the context was created with");
+  int rc = cocons_ctx_set_z(v.c, REAL(z));
   UNPROTECT(1);
   raise(rc);
   return R_NilValue;
 }
 
 SEXP _cocons_ctx_set_xbetas(SEXP ptr, SEXP xbS) {
+  const ctx_view v = view_of(ptr);
   SEXP xb = PROTECT(as_real(xbS));
-  int rc = cocons_ctx_set_xbetas(ctx_of(ptr), Rf_isMatrix(xb) ? Rf_ncols(xb) : 1, REAL(xb));
+  need(rows_of(xb) == v.n, "ctx_set_xbetas", "x_betas must have n rows");
+  int rc = cocons_ctx_set_xbetas(v.c, Rf_isMatrix(xb) ? Rf_ncols(xb) : 1, REAL(xb));
   UNPROTECT(1);
   raise(rc);
   return R_NilValue;
@@ -220,13 +278,16 @@ SEXP _cocons_ctx_set_xbetas(SEXP ptr, SEXP xbS) {
 
 /* c(status, logdet, logdet_w, rank, quad...) on the resident data */
 SEXP _cocons_ctx_n2ll(SEXP ptr, SEXP kindS, SEXP thetaS, SEXP pS, SEXP rS, SEXP limS, SEXP meanS) {
+  const ctx_view v = view_of(ptr);
   SEXP lim = PROTECT(as_real(limS)), mean = PROTECT(as_real(meanS));
   const int p = Rf_asInteger(pS), r = Rf_asInteger(rS);
+  need(p == v.p && r == v.r, "ctx_n2ll", "p / r differ from the context's");
+  check_limits("ctx_n2ll", lim);
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, 4 + r));
   double logdet = R_NaReal, ldw = 0.0;
   int rank = 0;
-  int rc = cocons_n2ll(ctx_of(ptr), Rf_asInteger(kindS), th, REAL(lim), LENGTH(mean) == p ? REAL(mean) : NULL, &logdet,
+  int rc = cocons_n2ll(v.c, Rf_asInteger(kindS), th, REAL(lim), LENGTH(mean) == p ? REAL(mean) : NULL, &logdet,
                        REAL(out) + 4, &ldw, &rank);
   free(th);
   REAL(out)[0] = rc, REAL(out)[1] = logdet, REAL(out)[2] = ldw, REAL(out)[3] = rank;
@@ -236,9 +297,12 @@ SEXP _cocons_ctx_n2ll(SEXP ptr, SEXP kindS, SEXP thetaS, SEXP pS, SEXP rS, SEXP 
 }
 
 SEXP _cocons_ctx_factor(SEXP ptr, SEXP parS, SEXP thetaS, SEXP pS, SEXP limS) {
+  const ctx_view v = view_of(ptr);
   SEXP lim = PROTECT(Rf_isNull(limS) ? limS : as_real(limS));
-  double* th = pack_theta(thetaS, Rf_asInteger(pS));
-  int rc = cocons_factor(ctx_of(ptr), Rf_asInteger(parS), th, Rf_isNull(lim) ? NULL : REAL(lim));
+  need(Rf_asInteger(pS) == v.p, "ctx_factor", "p differs from the context's");
+  if (!Rf_isNull(lim)) check_limits("ctx_factor", lim);
+  double* th = pack_theta(thetaS, v.p);
+  int rc = cocons_factor(v.c, Rf_asInteger(parS), th, Rf_isNull(lim) ? NULL : REAL(lim));
   free(th);
   UNPROTECT(1);
   raise(rc);
@@ -246,8 +310,11 @@ SEXP _cocons_ctx_factor(SEXP ptr, SEXP parS, SEXP thetaS, SEXP pS, SEXP limS) {
 }
 
 SEXP _cocons_ctx_profile_betas(SEXP ptr, SEXP kindS, SEXP qS) {
-  SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(qS)));
-  int rc = cocons_profile_betas(ctx_of(ptr), Rf_asInteger(kindS), REAL(out));
+  const ctx_view v = view_of(ptr);
+  const int kind = Rf_asInteger(kindS), q = Rf_asInteger(qS);
+  need(q == (kind == COCONS_PROFILE ? v.q : v.p), "ctx_profile_betas", "q is not the number of mean columns");
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, q));
+  int rc = cocons_profile_betas(v.c, kind, REAL(out));
   UNPROTECT(1);
   raise(rc);
   return out;
@@ -255,11 +322,13 @@ SEXP _cocons_ctx_profile_betas(SEXP ptr, SEXP kindS, SEXP qS) {
 
 /* list(stochastic, explained) for cocoPredict (R/predict.R:150-173) */
 SEXP _cocons_ctx_predict(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP residS) {
+  const ctx_view v = view_of(ptr);
   SEXP lp = PROTECT(as_real(locsPredS)), xp = PROTECT(as_real(xPredS)), resid = PROTECT(as_real(residS));
-  const int m = Rf_nrows(lp);
+  const int m = check_pred_sites("ctx_predict", &v, lp, xp);
+  need(XLENGTH(resid) == v.n, "ctx_predict", "the residual must have n elements");
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
   SEXP sto = PROTECT(Rf_allocVector(REALSXP, m)), expl = PROTECT(Rf_allocVector(REALSXP, m));
-  int rc = cocons_predict(ctx_of(ptr), m, REAL(lp), REAL(xp), REAL(resid), REAL(sto), REAL(expl));
+  int rc = cocons_predict(v.c, m, REAL(lp), REAL(xp), REAL(resid), REAL(sto), REAL(expl));
   SET_VECTOR_ELT(out, 0, sto);
   SET_VECTOR_ELT(out, 1, expl);
   UNPROTECT(6);
@@ -271,25 +340,27 @@ SEXP _cocons_ctx_predict(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP residS) {
 
 /* attach ref_taper (its colindices / rowpointers / entries slots, R/optim.R:376-379) */
 SEXP _cocons_ctx_set_taper(SEXP ptr, SEXP colS, SEXP rowS, SEXP entriesS) {
+  const ctx_view v = view_of(ptr);
   SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS)), ent = PROTECT(as_real(entriesS));
-  int rc = (XLENGTH(ent) == XLENGTH(col))
-               ? cocons_ctx_set_taper(ctx_of(ptr), INTEGER(col), INTEGER(row), REAL(ent), XLENGTH(col))
-               : -100;
+  need(XLENGTH(ent) == XLENGTH(col), "ctx_set_taper", "entries and colindices differ in length");
+  need(LENGTH(row) == v.n + 1, "ctx_set_taper", "rowpointers must have n + 1 elements");
+  int rc = cocons_ctx_set_taper(v.c, INTEGER(col), INTEGER(row), REAL(ent), XLENGTH(col));
   UNPROTECT(3);
-  if (rc == -100) Rf_error("ctx_set_taper: entries and colindices differ in length");
   raise(rc);
   return R_NilValue;
 }
 
 /* c(status, logdet, quad...) of the tapered model (R/neg2loglikelihood.R:20-108) */
 SEXP _cocons_ctx_n2ll_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP rS, SEXP limS, SEXP meanS) {
+  const ctx_view v = view_of(ptr);
   SEXP lim = PROTECT(as_real(limS)), mean = PROTECT(as_real(meanS));
   const int p = Rf_asInteger(pS), r = Rf_asInteger(rS);
+  need(p == v.p && r == v.r, "ctx_n2ll_taper", "p / r differ from the context's");
+  check_limits("ctx_n2ll_taper", lim);
   double* th = pack_theta(thetaS, p);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, 2 + r));
   double logdet = R_NaReal;
-  int rc = cocons_n2ll_taper(ctx_of(ptr), th, REAL(lim), LENGTH(mean) == p ? REAL(mean) : NULL, &logdet,
-                             REAL(out) + 2);
+  int rc = cocons_n2ll_taper(v.c, th, REAL(lim), LENGTH(mean) == p ? REAL(mean) : NULL, &logdet, REAL(out) + 2);
   free(th);
   REAL(out)[0] = rc, REAL(out)[1] = logdet;
   UNPROTECT(3);
@@ -298,9 +369,12 @@ SEXP _cocons_ctx_n2ll_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP rS, SEXP limS, 
 }
 
 SEXP _cocons_ctx_factor_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP limS) {
+  const ctx_view v = view_of(ptr);
   SEXP lim = PROTECT(as_real(limS));
-  double* th = pack_theta(thetaS, Rf_asInteger(pS));
-  int rc = cocons_factor_taper(ctx_of(ptr), th, REAL(lim));
+  need(Rf_asInteger(pS) == v.p, "ctx_factor_taper", "p differs from the context's");
+  check_limits("ctx_factor_taper", lim);
+  double* th = pack_theta(thetaS, v.p);
+  int rc = cocons_factor_taper(v.c, th, REAL(lim));
   free(th);
   UNPROTECT(1);
   raise(rc);
@@ -311,29 +385,31 @@ SEXP _cocons_ctx_factor_taper(SEXP ptr, SEXP thetaS, SEXP pS, SEXP limS) {
  * those of pred_taper BEFORE the covariance is multiplied in */
 SEXP _cocons_ctx_predict_taper(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP colS, SEXP rowS, SEXP entriesS,
                                SEXP residS) {
+  const ctx_view v = view_of(ptr);
   SEXP lp = PROTECT(as_real(locsPredS)), xp = PROTECT(as_real(xPredS)), resid = PROTECT(as_real(residS));
   SEXP col = PROTECT(as_int(colS)), row = PROTECT(as_int(rowS)), ent = PROTECT(as_real(entriesS));
-  const int m = Rf_nrows(lp);
+  const int m = check_pred_sites("ctx_predict_taper", &v, lp, xp);
+  need(LENGTH(row) == m + 1 && XLENGTH(ent) == XLENGTH(col), "ctx_predict_taper", "inconsistent pattern");
+  need(XLENGTH(resid) == v.n, "ctx_predict_taper", "the residual must have n elements");
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
   SEXP sto = PROTECT(Rf_allocVector(REALSXP, m)), expl = PROTECT(Rf_allocVector(REALSXP, m));
-  int rc = (LENGTH(row) == m + 1 && XLENGTH(ent) == XLENGTH(col))
-               ? cocons_predict_taper(ctx_of(ptr), m, REAL(lp), REAL(xp), INTEGER(col), INTEGER(row), REAL(ent),
-                                      XLENGTH(col), REAL(resid), REAL(sto), REAL(expl))
-               : -100;
+  int rc = cocons_predict_taper(v.c, m, REAL(lp), REAL(xp), INTEGER(col), INTEGER(row), REAL(ent), XLENGTH(col),
+                                REAL(resid), REAL(sto), REAL(expl));
   SET_VECTOR_ELT(out, 0, sto);
   SET_VECTOR_ELT(out, 1, expl);
   UNPROTECT(9);
-  if (rc == -100) Rf_error("ctx_predict_taper: inconsistent pattern");
   raise(rc);
   return out;
 }
 
 /* n x k draws L eps for cocoSim (R/sim.R:162-172); eps comes from R's own rnorm */
 SEXP _cocons_ctx_sim(SEXP ptr, SEXP epsS) {
+  const ctx_view v = view_of(ptr);
   SEXP eps = PROTECT(as_real(epsS));
+  need(Rf_isMatrix(eps) && Rf_nrows(eps) == v.n, "ctx_sim", "eps must be an n x k matrix");
   const int n = Rf_nrows(eps), k = Rf_ncols(eps);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, k));
-  int rc = cocons_sim(ctx_of(ptr), k, REAL(eps), REAL(out));
+  int rc = cocons_sim(v.c, k, REAL(eps), REAL(out));
   UNPROTECT(2);
   raise(rc);
   return out;
@@ -341,10 +417,13 @@ SEXP _cocons_ctx_sim(SEXP ptr, SEXP epsS) {
 
 /* m x k conditional draws (R/sim.R:87-121) */
 SEXP _cocons_ctx_sim_cond(SEXP ptr, SEXP locsPredS, SEXP xPredS, SEXP epsS) {
+  const ctx_view v = view_of(ptr);
   SEXP lp = PROTECT(as_real(locsPredS)), xp = PROTECT(as_real(xPredS)), eps = PROTECT(as_real(epsS));
-  const int m = Rf_nrows(lp), k = Rf_ncols(eps);
+  const int m = check_pred_sites("ctx_sim_cond", &v, lp, xp);
+  need(Rf_isMatrix(eps) && Rf_nrows(eps) == m, "ctx_sim_cond", "eps must be an nrow(locs_pred) x k matrix");
+  const int k = Rf_ncols(eps);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, m, k));
-  int rc = cocons_sim_cond(ctx_of(ptr), m, REAL(lp), REAL(xp), k, REAL(eps), REAL(out));
+  int rc = cocons_sim_cond(v.c, m, REAL(lp), REAL(xp), k, REAL(eps), REAL(out));
   UNPROTECT(4);
   raise(rc);
   return out;

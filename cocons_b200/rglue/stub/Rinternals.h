@@ -13,6 +13,7 @@ typedef int Rboolean;
 #define INTSXP 13
 #define VECSXP 19
 #define STRSXP 16
+#define EXTPTRSXP 22
 extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 extern double R_NaReal;
 double* REAL(SEXP);

@@ -85,6 +85,9 @@ int cocons_qr_rank(const double* x, int64_t n, int64_t p, double tol);
 int cocons_ctx_create(int device, int64_t n, int64_t p, int64_t r, const double* locs, const double* x_covariates,
                       const double* z, void* stream, cocons_ctx** out);
 void cocons_ctx_destroy(cocons_ctx* ctx);
+/* dims4 = {n, p, r, q} of the resident data (q = 0 until cocons_ctx_set_xbetas); lets the .Call glue refuse
+ * arguments whose shapes do not match the context before any pointer is handed to the device */
+int cocons_ctx_dims(cocons_ctx* ctx, int64_t* dims4);
 
 /* replace z (n x r, same r) - e.g. the REML contrasts of R/optim.R:311 */
 int cocons_ctx_set_z(cocons_ctx* ctx, const double* z);
