@@ -4,8 +4,15 @@
  *
  * Build inside the R package:  R CMD SHLIB cocons_glue.c -L<dir> -lcocons_b200 -o cocons.so
  * (see INTEGRATION.md).  R is not available in the build image of this repository, so here the
- * file is only syntax-checked against rglue/stub/ (tests/test_host.py); every numeric path it
- * calls is exercised through the same C ABI from Python.
+ * file is compiled against the declarations in rglue/stub/ and EXECUTED against a miniature of R's
+ * C API (tests/rmock: garbage collection at every allocation, PROTECT-stack and malloc accounting,
+ * Rf_error unwinding) by tests/test_rglue.py - on the CPU for registration, argument handling and
+ * error paths, on the GPU (-m gpu) for the same .Call sequences an R session makes, against the goldens.
+ *
+ * Every argument check that can raise an R error runs before anything is malloc'd (Rf_error does
+ * not return), and every shape is checked before a pointer is handed to the library: the
+ * reference's Rcpp code reads matrices through unchecked operator(), a mismatch here would make
+ * the device read past a host buffer.
  *
  * Conventions kept from the reference:
  *   - `theta` is a named list; aspects are looked up BY NAME ("std.dev","scale","aniso","tilt",

@@ -1,6 +1,7 @@
-/* SYNTAX-CHECK STUB ONLY.  R is not installed in the build image, so cocons_glue.c is
- * compiled with -fsyntax-only against these declarations (the subset of R's C API it uses,
- * with R's documented prototypes).  A real build uses R's own <Rinternals.h>. */
+/* STAND-IN DECLARATIONS ONLY.  R is not installed in the build image, so cocons_glue.c is
+ * compiled against these declarations (the subset of R's C API it uses, with R's documented
+ * prototypes) and linked, for the tests, with the miniature runtime in tests/rmock/rmock.c.
+ * A real build uses R's own <Rinternals.h>. */
 #ifndef COCONS_STUB_RINTERNALS_H
 #define COCONS_STUB_RINTERNALS_H
 #include <stddef.h>
