@@ -5,11 +5,13 @@
 // (tests/test_host_emul.py).  Nothing under cocons_b200/ includes or links this; the product library has no
 // CPU path (every computing entry returns COCONS_ERR_NO_DEVICE without an sm_100 device).
 //
-// Model: a kernel launch `k<<<grid, block, 0, st>>>(args)` is rewritten by the test (tests/host_emul/build.py)
-// into emul::launch(grid, block, has_barrier, [&] { k(args); }).  Blocks run one after another.  A kernel
-// without __syncthreads() runs its threads one after another too; one with barriers gets `block` OS threads
-// that live for the whole launch and meet at a barrier that, like the hardware's, counts exited threads as
-// arrived.  __shared__ becomes `static` (one block at a time, so one copy is what a block sees).
+// Model: a kernel launch `k<<<grid, block, smem, st>>>(args)` is rewritten by the test (tests/host_emul/build.py)
+// into emul::launch(grid, block, has_barrier, smem, [&] { k(args); }); `extern __shared__ T name[];` becomes a
+// pointer to the launch's dynamic shared memory.  Blocks run one after another.  A kernel
+// without __syncthreads() runs its threads one after another too; in one with barriers every CUDA thread is a
+// fiber, and one round-robin pass over the live fibers is one barrier phase (a thread that has left the kernel
+// counts as arrived, as on the hardware).  __shared__ becomes `static` (one block at a time, so one copy is what
+// a block sees).  Single OS thread, deterministic.
 // Round-to-nearest intrinsics map to the plain IEEE operation (compile with -ffp-contract=off), __fma_rn to
 // fma(); exp / sin / cos / log come from glibc, which legitimately differs from CUDA's libm by an ulp.
 #ifndef COCONS_TEST_CUDA_EMUL_H
@@ -17,13 +19,11 @@
 
 #include <algorithm>
 #include <cmath>
-#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
-#include <thread>
+#include <ucontext.h>
 #include <utility>
 #include <vector>
 
@@ -34,103 +34,252 @@
 #define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
   constexpr dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct double2 {
+  double x, y;
+};
+
+// host memory is "device" memory here: the handful of runtime calls the launch helpers of solve.cu make
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
 inline const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+template <class T>
+cudaError_t cudaMalloc(T** p, size_t bytes) {
+  *p = static_cast<T*>(std::malloc(bytes ? bytes : 1));
+  return *p ? cudaSuccess : 2;
+}
+inline cudaError_t cudaFree(void* p) {
+  std::free(p);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+  std::memmove(d, s, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memmove(d, s, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+  std::memset(d, v, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaGetDevice(int* d) {
+  *d = 0;
+  return cudaSuccess;
+}
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+  *v = 148;
+  return cudaSuccess;
+}
+template <class F>
+cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
+  return cudaSuccess;
+}
+template <class F>
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) {
+  *n = 1;
+  return cudaSuccess;
+}
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) {
+  *lo = 0, *hi = -1;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) {
+  *s = nullptr;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
+  *e = nullptr;
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
+  *e = nullptr;
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }  // launches are synchronous:
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // program order
+inline cudaError_t cudaLaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) {
+  std::fprintf(stderr, "host emulation: cooperative launches are driven by the test harness (grid of one block)\n");
+  std::abort();
+}
 
 namespace emul {
 
-// __syncthreads() of one block: releases when every thread of the block has either arrived or left the kernel
-class BlockBarrier {
- public:
-  explicit BlockBarrier(unsigned n) : n_(n) {}
-  void sync() {
-    std::unique_lock<std::mutex> lk(m_);
-    ++waiting_;
-    release_or_wait(lk);
-  }
-  // the calling thread has returned from the kernel: counts as arrived for every later barrier of this block;
-  // returns once the whole block has finished (the next block reuses the static "shared" arrays)
-  void leave_block() {
-    std::unique_lock<std::mutex> lk(m_);
-    ++exited_;
-    if (exited_ == n_) {
-      exited_ = 0;
-      ++block_gen_;
-      cv_.notify_all();
-      return;
-    }
-    if (waiting_ && waiting_ + exited_ == n_) {
-      waiting_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    }
-    const unsigned long g = block_gen_;
-    cv_.wait(lk, [&] { return block_gen_ != g; });
-  }
-
- private:
-  void release_or_wait(std::unique_lock<std::mutex>& lk) {
-    if (waiting_ + exited_ == n_) {
-      waiting_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    } else {
-      const unsigned long g = gen_;
-      cv_.wait(lk, [&] { return gen_ != g; });
-    }
-  }
-  std::mutex m_;
-  std::condition_variable cv_;
-  unsigned n_, waiting_ = 0, exited_ = 0;
-  unsigned long gen_ = 0, block_gen_ = 0;
-};
-
 struct ThreadCtx {
   dim3 tid, bid, bdim, gdim;
-  BlockBarrier* bar = nullptr;
+  void* dyn_smem = nullptr;  // the launch's dynamic shared memory (one block at a time)
+  bool in_block = false;     // inside a block that runs on fibers (has barriers)
 };
-inline thread_local ThreadCtx ctx;
+inline ThreadCtx ctx;
 inline long launches = 0, barrier_launches = 0;
 
+// One block of a kernel with barriers: every CUDA thread is a fiber (ucontext) of the calling OS thread.  The
+// scheduler resumes the runnable fibers one after another; a fiber runs until it has to wait:
+//   WAIT_BLOCK  __syncthreads(): released when every live thread of the block waits there
+//   WAIT_WARP   __syncwarp() and the warp-collective instructions (mma.sync): released when every live lane of the
+//               warp waits there
+//   (RUNNABLE)  a polling loop (mbarrier.try_wait) gives the turn away and is resumed in the next pass
+// A thread that has left the kernel counts as arrived, as on the hardware.  Nothing runnable while threads are
+// alive is a deadlock and ends the test with a message.  Deterministic; a barrier costs `block` context switches.
+class FiberBlock {
+ public:
+  enum State : unsigned char { RUNNABLE, WAIT_BLOCK, WAIT_WARP, DONE };
+  static constexpr size_t kStack = 256 * 1024;
+  explicit FiberBlock(unsigned nt)
+      : nt_(nt), fibers_(nt), tctx_(nt), state_(nt, DONE), ops_(nt, 0), xa_(((nt + 31) / 32) * 64), xb_(xa_.size()) {
+    stacks_ = static_cast<char*>(std::malloc(kStack * nt));
+    if (!stacks_) std::abort();
+  }
+  ~FiberBlock() { std::free(stacks_); }
+  FiberBlock(const FiberBlock&) = delete;
+
+  template <class Body>
+  void run(const Body& body, dim3 bid, dim3 block, dim3 grid, void* dyn) {
+    body_ = [](void* b) { (*static_cast<const Body*>(b))(); };
+    body_arg_ = const_cast<Body*>(&body);
+    current_block_ = this;
+    for (unsigned t = 0; t < nt_; ++t) {
+      tctx_[t].tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      tctx_[t].bid = bid, tctx_[t].bdim = block, tctx_[t].gdim = grid, tctx_[t].dyn_smem = dyn;
+      tctx_[t].in_block = true;
+      state_[t] = RUNNABLE;
+      ops_[t] = 0;
+      getcontext(&fibers_[t]);
+      fibers_[t].uc_stack.ss_sp = stacks_ + kStack * t;
+      fibers_[t].uc_stack.ss_size = kStack;
+      fibers_[t].uc_link = &main_;
+      makecontext(&fibers_[t], reinterpret_cast<void (*)()>(&FiberBlock::trampoline), 0);
+    }
+    unsigned live = nt_;
+    or_acc_ = 0;
+    while (live) {
+      // releases
+      bool all_at_block = true;
+      for (unsigned t = 0; t < nt_; ++t)
+        if (state_[t] == RUNNABLE || state_[t] == WAIT_WARP) all_at_block = false;
+      if (all_at_block) {
+        for (unsigned t = 0; t < nt_; ++t)
+          if (state_[t] == WAIT_BLOCK) state_[t] = RUNNABLE;
+        or_result_ = or_acc_;  // what __syncthreads_or() of the phase just completed returns
+        or_acc_ = 0;
+      }
+      for (unsigned w0 = 0; w0 < nt_; w0 += 32) {
+        const unsigned w1 = w0 + 32 < nt_ ? w0 + 32 : nt_;
+        bool any = false, all = true;
+        for (unsigned t = w0; t < w1; ++t) {
+          if (state_[t] == WAIT_WARP) any = true;
+          if (state_[t] == RUNNABLE || state_[t] == WAIT_BLOCK) all = false;
+        }
+        if (any && all)
+          for (unsigned t = w0; t < w1; ++t)
+            if (state_[t] == WAIT_WARP) state_[t] = RUNNABLE;
+      }
+      bool progressed = false;
+      for (unsigned t = 0; t < nt_; ++t) {
+        if (state_[t] != RUNNABLE) continue;
+        progressed = true;
+        cur_ = t;
+        ctx = tctx_[t];
+        swapcontext(&main_, &fibers_[t]);
+        if (state_[t] == DONE) --live;
+      }
+      if (!progressed && live) {
+        std::fprintf(stderr, "host emulation: deadlock - %u live thread(s) of block (%u,%u,%u), none runnable "
+                     "(a barrier that not every thread of the block / warp reaches)\n", live, bid.x, bid.y, bid.z);
+        std::abort();
+      }
+    }
+    ctx.in_block = false;
+    current_block_ = nullptr;
+  }
+  // from a fiber: wait in `state` (WAIT_BLOCK / WAIT_WARP), or give the turn away (RUNNABLE: a polling loop)
+  int wait(State state, int pred = 0) {
+    if (pred) or_acc_ = 1;
+    const unsigned me = cur_;
+    state_[me] = state;
+    swapcontext(&fibers_[me], &main_);
+    return or_result_;
+  }
+  void poll() {
+    if (++polls_ > (1ull << 33)) {
+      std::fprintf(stderr, "host emulation: a polling loop does not end\n");
+      std::abort();
+    }
+    wait(RUNNABLE);
+  }
+  // warp-collective exchange (mma.sync operands): every lane deposits, the warp meets, every lane reads.  Two
+  // slots by the parity of the lane's collective-operation count: a lane can be at most one operation ahead of
+  // the slowest lane of its warp (it has to meet the warp again), so the slot being read is never overwritten
+  void exchange(double a, double b, const double*& all_a, const double*& all_b) {
+    const unsigned t = cur_, w = t >> 5, lane = t & 31, par = ops_[t]++ & 1;
+    double* sa = xa_.data() + (w * 2 + par) * 32;
+    double* sb = xb_.data() + (w * 2 + par) * 32;
+    sa[lane] = a, sb[lane] = b;
+    wait(WAIT_WARP);
+    all_a = sa, all_b = sb;
+  }
+  unsigned lane() const { return cur_ & 31; }
+  static FiberBlock* current() { return current_block_; }
+
+ private:
+  static void trampoline() {
+    FiberBlock* b = current_block_;
+    b->body_(b->body_arg_);
+    b->state_[b->cur_] = DONE;  // falls back to main_ through uc_link
+  }
+  static inline FiberBlock* current_block_ = nullptr;
+  unsigned nt_, cur_ = 0;
+  std::vector<ucontext_t> fibers_;
+  std::vector<ThreadCtx> tctx_;
+  std::vector<unsigned char> state_;
+  std::vector<unsigned> ops_;
+  std::vector<double> xa_, xb_;
+  ucontext_t main_;
+  char* stacks_ = nullptr;
+  void (*body_)(void*) = nullptr;
+  void* body_arg_ = nullptr;
+  int or_acc_ = 0, or_result_ = 0;
+  unsigned long long polls_ = 0;
+};
+
 template <class Body>
-void launch(dim3 grid, dim3 block, bool has_barrier, Body&& body) {
+void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& body) {
   ++launches;
+  std::vector<double> smem(smem_bytes / sizeof(double) + 2);
+  void* const dyn = smem.data();
   const unsigned nt = block.x * block.y * block.z;
-  auto thread_id = [&](unsigned t) { return dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); };
   if (!has_barrier) {
     for (unsigned bz = 0; bz < grid.z; ++bz)
       for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx)
           for (unsigned t = 0; t < nt; ++t) {
-            ctx.tid = thread_id(t), ctx.bid = dim3(bx, by, bz), ctx.bdim = block, ctx.gdim = grid, ctx.bar = nullptr;
+            ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            ctx.bid = dim3(bx, by, bz), ctx.bdim = block, ctx.gdim = grid, ctx.dyn_smem = dyn, ctx.in_block = false;
             body();
           }
     return;
   }
   ++barrier_launches;
-  BlockBarrier bar(nt);
-  std::vector<std::thread> pool;
-  pool.reserve(nt);
-  for (unsigned t = 0; t < nt; ++t)
-    pool.emplace_back([&, t] {
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            ctx.tid = thread_id(t), ctx.bid = dim3(bx, by, bz), ctx.bdim = block, ctx.gdim = grid, ctx.bar = &bar;
-            body();
-            bar.leave_block();
-          }
-    });
-  for (auto& th : pool) th.join();
+  FiberBlock fb(nt);
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) fb.run(body, dim3(bx, by, bz), block, grid, dyn);
 }
 
 }  // namespace emul
@@ -140,12 +289,119 @@ void launch(dim3 grid, dim3 block, bool has_barrier, Body&& body) {
 #define blockDim (emul::ctx.bdim)
 #define gridDim (emul::ctx.gdim)
 
-inline void __syncthreads() {
-  if (!emul::ctx.bar) {
-    std::fprintf(stderr, "host emulation: __syncthreads() in a kernel launched without barrier support\n");
+inline emul::FiberBlock* emul_block() {
+  if (!emul::ctx.in_block || !emul::FiberBlock::current()) {
+    std::fprintf(stderr, "host emulation: a barrier in a kernel launched without barrier support\n");
     std::abort();
   }
-  emul::ctx.bar->sync();
+  return emul::FiberBlock::current();
+}
+inline int emul_barrier(int pred) { return emul_block()->wait(emul::FiberBlock::WAIT_BLOCK, pred); }
+inline void __syncthreads() { emul_barrier(0); }
+inline void __syncwarp() { emul_block()->wait(emul::FiberBlock::WAIT_WARP); }
+
+inline int __syncthreads_or(int pred) { return emul_barrier(pred); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) {}
+template <class T>
+T __ldg(const T* p) {
+  return *p;
+}
+template <class T>
+T __ldcg(const T* p) {
+  return *p;
+}
+template <class T>
+T __ldcv(const T* p) {
+  return *p;
+}
+template <class T>
+T __ldcs(const T* p) {
+  return *p;
+}
+template <class T>
+void __stcs(T* p, T v) {
+  *p = v;
+}
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline double __shfl_sync(unsigned, double, int) {
+  std::fprintf(stderr, "host emulation: partial-warp shuffles are not emulated (potrf_tile_kernel, COCONS_POTRF=1)\n");
+  std::abort();
+}
+// offset of a shared-memory object inside the launch's dynamic shared memory (what the 32-bit shared-window
+// address is used for in the kernels: mbarrier and bulk-copy operands)
+inline size_t __cvta_generic_to_shared(const void* p) {
+  return (size_t)(static_cast<const char*>(p) - static_cast<const char*>(emul::ctx.dyn_smem));
+}
+
+// ---- stand-ins for the inline-PTX helper functions of the kernels (tests/host_emul/build.py replaces the body of a
+//      __device__ helper made of one asm statement by a call to emul::ptx_<name> with the same arguments) ---------
+namespace emul {
+// mma.sync.aligned.m8n8k4.row.col.f64: a = A[g][c4], b = B[c4][g], {d0, d1} = D[g][2 c4 + {0, 1}], g = lane / 4,
+// c4 = lane % 4; the four products of an entry are accumulated in k order (the hardware's order is not documented;
+// the tests compare at a tolerance)
+inline void ptx_dmma884(double& d0, double& d1, double a, double b) {
+  FiberBlock* fb = emul_block();
+  const unsigned lane = fb->lane(), g = lane >> 2, c4 = lane & 3;
+  const double *A, *B;
+  fb->exchange(a, b, A, B);
+  for (unsigned k = 0; k < 4; ++k) {
+    d0 = std::fma(A[g * 4 + k], B[(2 * c4) * 4 + k], d0);
+    d1 = std::fma(A[g * 4 + k], B[(2 * c4 + 1) * 4 + k], d1);
+  }
+}
+// mbarrier in 8 bytes of shared memory: arrivals still expected in this phase, transaction bytes outstanding, phase
+struct MBar {
+  uint16_t expected, pending;
+  int32_t tx : 31;
+  uint32_t phase : 1;
+};
+static_assert(sizeof(MBar) == 8, "an mbarrier is one 64-bit word");
+inline MBar* mbar_at(uint32_t off) { return reinterpret_cast<MBar*>(static_cast<char*>(ctx.dyn_smem) + off); }
+inline void mbar_check(MBar* m) {
+  if (m->pending == 0 && m->tx == 0) m->phase ^= 1, m->pending = m->expected;
+}
+inline void ptx_mbar_init(uint32_t bar, uint32_t count) {
+  MBar* m = mbar_at(bar);
+  m->expected = m->pending = (uint16_t)count, m->tx = 0, m->phase = 0;
+}
+inline void ptx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  MBar* m = mbar_at(bar);
+  m->tx += (int32_t)bytes, m->pending -= 1;
+  mbar_check(m);
+}
+inline void ptx_mbar_arrive(uint32_t bar) {
+  MBar* m = mbar_at(bar);
+  m->pending -= 1;
+  mbar_check(m);
+}
+inline void ptx_mbar_arrive_after(uint32_t bar, double, double, uint32_t) { ptx_mbar_arrive(bar); }
+inline void ptx_mbar_wait(uint32_t bar, uint32_t parity) {  // until the phase with this parity has completed
+  while (mbar_at(bar)->phase == parity) emul_block()->poll();
+}
+// cp.async.bulk global -> shared with complete_tx on the barrier; synchronous here
+inline void ptx_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  std::memcpy(static_cast<char*>(ctx.dyn_smem) + dst, src, bytes);
+  MBar* m = mbar_at(bar);
+  m->tx -= (int32_t)bytes;
+  mbar_check(m);
+}
+inline unsigned ptx_ld_acquire_u32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void ptx_st_release_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long ptx_ld_relaxed_u64(const double* p) {
+  return __atomic_load_n(reinterpret_cast<const unsigned long long*>(p), __ATOMIC_RELAXED);
+}
+}  // namespace emul
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int* p, int expected, int desired) {
+  __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return expected;
+}
+inline double __longlong_as_double(long long v) {
+  double d;
+  std::memcpy(&d, &v, sizeof d);
+  return d;
 }
 
 // IEEE round-to-nearest intrinsics (the build uses -ffp-contract=off, so a * b + c is never fused behind our back)

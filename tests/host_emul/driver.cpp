@@ -7,10 +7,15 @@
 //   emu_ctx_lower     assemble_and_factor()   capi.cu  (Morton-ordered, padded, lower triangle only)
 //   emu_dist_slabs    cocons_dist_assemble()  cocons_b200/csrc/dist.cu (one rank's column panels, both launch modes)
 //   emu_taper_*       taper_entries_host() / the TS_LOWER sink of assemble_and_factor(taper = true)
+//   emu_forward_solve forward_solve_ws() / forward_solve()  cocons_b200/csrc/solve.cu (K6b dataflow kernel through the
+//                     library's own launcher; K6 cooperative kernel on a grid of one block; the two-kernel-per-step path)
+//   emu_logdet / emu_gram   launch_logdet() / launch_gram()
 #include "cuda_runtime.h"  // the emulation shim (found first through -I tests/host_emul)
 
 #include ASSEMBLY_INC
 #include TAPER_INC
+#include SOLVE_INC
+#include CHOL_INC
 
 namespace cocons {
 void set_error(const char*, ...) {}
@@ -18,6 +23,17 @@ void note_launch(int) {}
 }  // namespace cocons
 
 using namespace cocons;
+
+namespace {
+template <int NR>
+void run_variant(int mode, const double* L, int64_t ld, const double* winv, double* B, double* Y, int64_t ldb,
+                 int64_t nt, int nr) {
+  if (mode == 1)
+    launch_fwd_steps<NR>(L, ld, winv, B, Y, ldb, nt, nr, nullptr);
+  else
+    emul::launch(dim3(1), dim3(256), true, 0, [&] { fwd_solve_coop_kernel<NR>(L, ld, winv, B, Y, ldb, nt, nr); });
+}
+}  // namespace
 
 extern "C" {
 
@@ -128,6 +144,84 @@ int emu_taper_lower(int64_t n, int64_t n_pad, int64_t p, const double* locs_sort
   launch_taper_entries(0, nnz, n, colindices, rowpointers, T, T, 1, mode, nu_fixed,
                        TaperSink{TS_LOWER, nullptr, taper, inv, A, n_pad, 0}, nullptr);
   return mode;
+}
+
+// L Y = B.  L: n_pad x n_pad lower factor, winv: the inverted diagonal tiles (n_pad / 128 of 128 x 128, zeros above the
+// diagonal), B: n_pad x (2 nrhs) - right-hand sides in the first nrhs columns, scratch behind them (the library's
+// contract); on return the first nrhs columns hold Y.  mode 0: dataflow kernel (K6b) through forward_solve_ws with a
+// workspace from solve_workspace_create; 1: the two-kernels-per-tile-step path; 2: the cooperative kernel (K6), one block.
+
+int emu_forward_solve(int64_t n_pad, const double* L, const double* winv, double* B, int nrhs, int mode) {
+  const int64_t ld = n_pad, ldb = n_pad, nt = n_pad / kTile;
+  if (mode == 0) {
+    CholWorkspace ws{};
+    int info = 0;
+    ws.winv = const_cast<double*>(winv);
+    ws.info = &info;
+    if (solve_workspace_create(n_pad, &ws) != 0) return -1;
+    forward_solve_ws(L, n_pad, ld, ws, B, ldb, nrhs, nullptr);
+    const int err = info ? info : (int)ws.solve_ctrl[2];
+    solve_workspace_destroy(&ws);
+    return err;
+  }
+  double* Y = B + (int64_t)nrhs * ldb;
+  for (int c0 = 0; c0 < nrhs; c0 += 8) {  // the dispatch of forward_solve()
+    const int nr = (nrhs - c0 < 8) ? nrhs - c0 : 8;
+    double *Bc = B + (int64_t)c0 * ldb, *Yc = Y + (int64_t)c0 * ldb;
+    if (nr == 1)
+      run_variant<1>(mode, L, ld, winv, Bc, Yc, ldb, nt, nr);
+    else if (nr == 2)
+      run_variant<2>(mode, L, ld, winv, Bc, Yc, ldb, nt, nr);
+    else if (nr <= 4)
+      run_variant<4>(mode, L, ld, winv, Bc, Yc, ldb, nt, nr);
+    else
+      run_variant<8>(mode, L, ld, winv, Bc, Yc, ldb, nt, nr);
+  }
+  std::memcpy(B, Y, sizeof(double) * (size_t)nrhs * (size_t)ldb);
+  return 0;
+}
+
+double emu_logdet(const double* L, int64_t n, int64_t ld) {
+  double out = 0.0;
+  launch_logdet(L, n, ld, &out, nullptr);
+  return out;
+}
+
+// G (k x k) = Y^T Y over the first n rows of the n_pad-leading-dimension block Y
+void emu_gram(const double* Y, int64_t n, int64_t ldy, int k, double* G) {
+  std::vector<double> buf(16 * 16 + 296 * 256);
+  launch_gram(Y, n, ldy, k, buf.data(), nullptr);
+  std::memcpy(G, buf.data(), sizeof(double) * k * k);
+}
+
+// ---- csrc/chol.cu --------------------------------------------------------------------------------------------------
+// chol_factor() itself (the look-ahead driver with its two streams: launches are synchronous here, so the program
+// order of the driver is the execution order).  A: n_pad x n_pad, lower triangle + whole diagonal tiles set;
+// winv receives the n_pad / 128 inverted diagonal tiles.  Returns dpotrf's info (0, or the first failing pivot).
+int emu_chol_factor(int64_t n_pad, double* A, double* winv) {
+  CholWorkspace ws{};
+  int info = 0;
+  ws.winv = winv, ws.info = &info;
+  chol_factor(A, n_pad, n_pad, ws, nullptr);
+  return info;
+}
+
+// one 128 x 128 diagonal tile: factor in place + explicit inverse (launch_potrf_tile: the blocked DMMA kernel K3b)
+int emu_potrf_tile(double* A, int64_t ld, double* winv, int first_index) {
+  int info = 0;
+  launch_potrf_tile(A, ld, winv, &info, first_index, nullptr);
+  return info;
+}
+
+// launch_gemm_nt: mode 0  C -= A B^T (128 x 64 tiles, optionally only the tiles on or below the diagonal),
+//                 mode 1  C  = A B^T (128 x 128 tiles)
+void emu_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* C, int64_t ldc, int lower_only) {
+  launch_gemm_nt(mode, M, N, K, A, lda, B, ldb, C, ldc, lower_only, nullptr);
+}
+
+int64_t emu_tile_count(int w, int ni, int njc, int lower_only) {
+  return w == 1 ? total_tiles<1>(ni, njc, lower_only) : total_tiles<2>(ni, njc, lower_only);
 }
 
 }  // extern "C"

@@ -1,11 +1,13 @@
-"""CPU checks of the SHIPPED assembly kernels, executed thread for thread on the host.
+"""CPU checks of the SHIPPED assembly and solve kernels, executed thread for thread on the host.
 
-cocons_b200/csrc/assembly.cu and taper.cu are compiled with g++ against the small CUDA execution-model shim in
+cocons_b200/csrc/assembly.cu, taper.cu and solve.cu are compiled with g++ against the small CUDA execution-model shim in
 tests/host_emul/ (launches rewritten mechanically, everything else as it ships) and run against the same goldens
 and the same 1e-12 bar as the GPU parity tests (tests/test_gpu_cov.py, tests/test_gpu_taper.py): the reference's
 operation order in the pair arithmetic (src/cocons_full.cpp:257-313), the staging of the column sites through
 shared memory, the tile / slice / slab index math of the resident and the block-cyclic layouts, the Morton
-ordering with the carried caller index of the coincident-pair quirk (:284-286), the CSR sinks of the tapered model.
+ordering with the carried caller index of the coincident-pair quirk (:284-286), the CSR sinks of the tapered model;
+the forward substitution (dataflow kernel with its work-unit table, cooperative kernel, two-kernel path), the
+log-determinant and the Gram reductions against LAPACK.
 This is test scaffolding: the product has no CPU path (tests/test_host.py::test_no_cpu_fallback_without_a_device),
 and the device build of the same source is what `-m gpu` measures.  What it cannot see is CUDA's own libm
 (exp / sin / cos differ from glibc's by an ulp) and anything about memory ordering on the device."""
@@ -70,11 +72,15 @@ def _case(emu, case):
 
 
 def test_the_rewrite_is_mechanical_and_complete(emu):
-    """every kernel of the two files is launched through the shim; the three with __syncthreads() get real threads"""
+    """every kernel of the four files is launched through the shim; those with barriers run on fibers"""
     assert emu._barriers == {"site_stage_kernel": False, "assemble_lower_kernel": True, "assemble_cross_kernel": True,
                              "symmetrize_kernel": True, "taper_site_stage_kernel": False,
-                             "taper_entries_kernel": False, "taper_pad_diag_kernel": False}
-    assert emu._rewritten == 7
+                             "taper_entries_kernel": False, "taper_pad_diag_kernel": False,
+                             "logdet_kernel": True, "fwd_solve_coop_kernel": True, "fwd_tile_solve_kernel": True,
+                             "fwd_tile_update_kernel": True, "fwd_solve_flow_kernel": True,
+                             "gram_partial_kernel": True, "gram_final_kernel": False,
+                             "gemm_nt_tma_kernel": True, "potrf_tile_kernel": True, "potrf_tile_blocked_kernel": True}
+    assert emu._rewritten == 17  # every <<<...>>> of assembly.cu, taper.cu, solve.cu and chol.cu
 
 
 def test_shipped_kernels_reproduce_the_goldens_on_the_host(emu, cov_cases):
@@ -278,3 +284,171 @@ def test_dense_sink_of_the_tapered_objective(emu, taper_cases):
     want[np.arange(n, n_pad), np.arange(n, n_pad)] = 1.0
     assert np.array_equal(A, want)
     assert relerr(entries, case["out"]) < TOL
+
+
+# ---- forward substitution, log-determinant, Gram reductions (csrc/solve.cu) ----------------------------------------
+def _factor_problem(T, seed):
+    """a well-conditioned lower factor of T x T tiles and its inverted diagonal tiles (zeros above the diagonal)"""
+    import scipy.linalg as sla
+    n_pad = 128 * T
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n_pad, 40))
+    L = np.linalg.cholesky(M @ M.T / 40 + np.eye(n_pad) * 2.0)
+    W = np.zeros((T, 128, 128))
+    for J in range(T):
+        W[J] = sla.solve_triangular(L[128 * J:128 * (J + 1), 128 * J:128 * (J + 1)], np.eye(128), lower=True)
+    winv = np.ascontiguousarray(np.stack([np.asfortranarray(W[J]).ravel(order="F") for J in range(T)]))
+    return n_pad, np.asfortranarray(L), winv
+
+
+def _emu_solve(emu, n_pad, L, winv, B, mode):
+    nrhs = B.shape[1]
+    buf = np.zeros((n_pad, 2 * nrhs), order="F")
+    buf[:, :nrhs] = B
+    assert emu.emu_forward_solve(n_pad, _p(L), _p(winv), _p(buf), nrhs, mode) == 0
+    return buf[:, :nrhs].copy()
+
+
+@pytest.mark.parametrize("T,nrhs", [(1, 1), (3, 2), (5, 3), (18, 1), (18, 5), (35, 11)])
+def test_forward_substitution_kernels_on_the_host(emu, T, nrhs):
+    """L Y = B by the dataflow kernel (K6b, through the library's own launcher and work-unit table), by the cooperative
+    kernel (K6) and by the two-kernels-per-step path, against LAPACK.  T = 18 and 35 give rows whose tile columns are
+    cut into two / three chunks (kSolveChunk = 16), nrhs = 11 takes two passes of the launcher (8 + 3)."""
+    import scipy.linalg as sla
+    n_pad, L, winv = _factor_problem(T, 100 + T)
+    B = np.random.default_rng(T).standard_normal((n_pad, nrhs))
+    want = sla.solve_triangular(L, B, lower=True)
+    scale = np.max(np.abs(want))
+    got = {mode: _emu_solve(emu, n_pad, L, winv, B, mode) for mode in ((0, 1, 2) if T <= 18 else (0,))}
+    for mode, Y in got.items():
+        assert np.max(np.abs(Y - want)) < 1e-12 * scale, (mode, np.max(np.abs(Y - want)) / scale)
+    # the same arithmetic in the cooperative kernel and in its two-kernel restatement: the same bits
+    if 1 in got:
+        assert np.array_equal(got[1], got[2])
+    # the dataflow kernel gives the same bits whatever the schedule was: here, twice
+    assert np.array_equal(got[0], _emu_solve(emu, n_pad, L, winv, B, 0))
+
+
+def test_logdet_and_gram_kernels_on_the_host(emu):
+    n_pad, L, _ = _factor_problem(5, 9)
+    n = n_pad - 37
+    assert abs(emu.emu_logdet(_p(L), n, n_pad) - np.sum(np.log(np.diag(L)[:n]))) < 1e-12 * n
+    Y = np.asfortranarray(np.random.default_rng(4).standard_normal((n_pad, 3)))
+    G = np.zeros((3, 3))
+    emu.emu_gram(_p(Y), n, n_pad, 3, _p(G))
+    want = Y[:n].T @ Y[:n]
+    assert np.max(np.abs(G - want)) < 1e-12 * np.max(np.abs(want)) and np.array_equal(G, G.T)
+
+
+# ---- blocked Cholesky (csrc/chol.cu): DMMA tile kernel, bulk-copy / mbarrier GEMM, look-ahead driver ----------------
+def _spd(n_pad, seed, shift=2.0):
+    M = np.random.default_rng(seed).standard_normal((n_pad, 40))
+    return M @ M.T / 40 + np.eye(n_pad) * shift
+
+
+def _lower_with_diagonal_tiles(S, fill=np.nan):
+    """what the assembly leaves behind: the lower triangle plus whole diagonal tiles; the rest is never read"""
+    n_pad = S.shape[0]
+    A = np.full((n_pad, n_pad), fill, order="F")
+    A[np.tril_indices(n_pad)] = S[np.tril_indices(n_pad)]
+    for J in range(n_pad // 128):
+        A[128 * J:128 * (J + 1), 128 * J:128 * (J + 1)] = S[128 * J:128 * (J + 1), 128 * J:128 * (J + 1)]
+    return A
+
+
+def test_ptx_helpers_are_the_ones_with_stand_ins(emu):
+    """rule (1) of rewrite_ptx: every inline-PTX helper of the kernels is mapped to a documented stand-in"""
+    assert emu.ptx_helpers == ["bulk_g2s", "dmma884", "ld_acquire_u32", "ld_relaxed_u64", "mbar_arrive",
+                               "mbar_arrive_after", "mbar_expect_tx", "mbar_init", "mbar_wait", "st_release_u32"]
+
+
+def test_diagonal_tile_kernel_on_the_host(emu):
+    """K3b: factor + explicit inverse of a 128 x 128 tile inside a larger matrix; dpotrf's info on a bad pivot"""
+    S = _spd(128, 1, shift=1.0)
+    big = np.full((300, 200), np.nan, order="F")
+    big[50:178, 30:158] = S
+    W = np.full((128, 128), np.nan, order="F")
+    tile = big[50:, 30:]  # element (0, 0) of the tile, leading dimension 300
+    assert emu.emu_potrf_tile(_p(tile), 300, _p(W), 1000) == 0
+    L = np.linalg.cholesky(S)
+    got = big[50:178, 30:158]
+    assert np.max(np.abs(got - L)) < 1e-14 and np.array_equal(np.triu(got, 1), np.zeros((128, 128)))
+    assert np.max(np.abs(W - np.linalg.inv(L))) < 1e-13 and np.array_equal(np.triu(W, 1), np.zeros((128, 128)))
+    assert np.all(np.isnan(big[:50])) and np.all(np.isnan(big[178:])) and np.all(np.isnan(big[:, :30]))
+    bad = S.copy()
+    bad[70, 70] = -1.0  # leading minor of order 71 is not positive definite
+    A = np.asfortranarray(bad)
+    assert emu.emu_potrf_tile(_p(A), 128, _p(W), 1000) == 1000 + 71
+
+
+@pytest.mark.parametrize("mode,M,N,K,lower", [(0, 384, 256, 48, 0), (0, 384, 384, 144, 1), (1, 256, 128, 128, 0)])
+def test_dmma_gemm_with_the_bulk_copy_pipeline_on_the_host(emu, mode, M, N, K, lower):
+    """K4 / K5: C (-)= A B^T.  Four-stage ring of bulk copies on mbarriers with a rotating producer warp, fragment
+    layout of mma.m8n8k4.f64, tile rasterisation (lower_only: tiles above the diagonal are not touched)."""
+    rng = np.random.default_rng(M + N + K)
+    A = np.asfortranarray(rng.standard_normal((M, K)))
+    B = np.asfortranarray(rng.standard_normal((N, K)))
+    C0 = np.asfortranarray(rng.standard_normal((M, N)))
+    C = C0.copy(order="F")
+    emu.emu_gemm_nt(mode, M, N, K, _p(A), M, _p(B), N, _p(C), M, lower)
+    want = A @ B.T if mode == 1 else C0 - A @ B.T
+    if lower:  # 128 x 64 tiles whose column block lies above the diagonal row block are skipped
+        bi, bj = np.arange(M)[:, None] // 128, np.arange(N)[None, :] // 64
+        touched = bi >= bj // 2
+        assert np.array_equal(C[~touched], C0[~touched])
+        assert np.max(np.abs(C[touched] - want[touched])) < 1e-12
+    else:
+        assert np.max(np.abs(C - want)) < 1e-12
+
+
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_cholesky_driver_on_the_host(emu, T):
+    """chol_factor(): panel steps (tile kernel, in-place panel solve X = A W^T, in-panel update), trailing updates
+    split for the look-ahead, against LAPACK; the strict upper triangle outside the diagonal tiles is never read"""
+    n_pad = 128 * T
+    S = _spd(n_pad, 40 + T)
+    A = _lower_with_diagonal_tiles(S)
+    W = np.full((T, 128, 128), np.nan)
+    assert emu.emu_chol_factor(n_pad, _p(A), _p(W)) == 0
+    L = np.linalg.cholesky(S)
+    assert np.max(np.abs(A[np.tril_indices(n_pad)] - L[np.tril_indices(n_pad)])) < 1e-13
+    for J in range(T):
+        WJ = W[J].T  # stored column-major
+        assert np.max(np.abs(WJ - np.linalg.inv(L[128 * J:128 * (J + 1), 128 * J:128 * (J + 1)]))) < 1e-12
+    bad = S.copy()
+    k = n_pad - 30
+    bad[k, k] = -5.0
+    A = _lower_with_diagonal_tiles(bad)
+    assert emu.emu_chol_factor(n_pad, _p(A), _p(W)) == k + 1  # dpotrf's info: order of the failing leading minor
+
+
+def test_one_objective_evaluation_by_the_shipped_kernels_on_the_host(emu):
+    """The whole hot path of one -2 loglik (R/neg2loglikelihood.R:183-222) - site stage, pairwise assembly in the
+    context's layout, blocked Cholesky, log-determinant, forward substitution, Gram reduction - each step by the
+    kernel source that ships, executed on the CPU, against the literal restatement of the reference (the same problem
+    __graft_entry__.smoke() evaluates on the GPU)."""
+    import cocons_b200 as cb
+    from oracle import rmirror
+    rng = np.random.default_rng(20261018)
+    n, p = 400, 3
+    locs = rng.uniform(-1, 1, (n, 2))
+    X = cb.getScale(np.column_stack([np.ones(n), (locs[:, 0] + 1) / 2, (locs[:, 1] + 1) / 2]))["std.covs"]
+    z = rng.standard_normal(n)
+    par_pos = {k: np.ones(p, dtype=bool) for k in ("mean", "std.dev", "scale", "aniso", "tilt", "smooth", "nugget")}
+    theta = np.array([0.1, 0.3, -0.2, -1.4, 0.35, -0.05, 1.8, -0.05, 0.25, 0.1, 0.2, -0.1, 0.3, -0.2, 0.1, 0.2, 0.3,
+                      -0.2, -4, 0.1, 0.1])
+    lim = [0.5, 2.5]
+    tl = cb.getModelLists(theta, par_pos, "diff")
+    n_pad, perm, A = _ctx_lower(emu, tl, locs, X, lim)
+    T = n_pad // 128
+    W = np.zeros((T, 128, 128))
+    assert emu.emu_chol_factor(n_pad, _p(A), _p(W)) == 0
+    logdet = emu.emu_logdet(_p(A), n, n_pad)
+    rhs = np.zeros((n_pad, 2), order="F")
+    rhs[:n, 0] = (z - X @ tl["mean"])[perm]
+    assert emu.emu_forward_solve(n_pad, _p(A), _p(W), _p(rhs), 1, 0) == 0
+    G = np.zeros((1, 1))
+    emu.emu_gram(_p(rhs), n, n_pad, 1, _p(G))
+    got = n * np.log(2 * np.pi) + 2 * logdet + G[0, 0]
+    want = rmirror.neg2loglik(theta, par_pos, locs, X, lim, z, n, (0.0, 0.0, 0.0))
+    assert abs(got - want) < 1e-10 * abs(want), (got, want)
