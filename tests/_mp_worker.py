@@ -1,5 +1,8 @@
-"""Worker of tests/test_multiproc.py: world-size-2 gloo run of the host-side multi-GPU logic with a
-numpy stand-in for the per-rank kernels (the CUDA kernels themselves are covered by -m gpu tests)."""
+"""Worker of tests/test_multiproc.py: world-size-2 gloo run of the host-side multi-GPU logic, with
+  * a numpy stand-in for the per-rank kernels (default), or
+  * COCONS_MP_EMULATED=<scratch dir>: the shipped csrc/dist.cu itself - its cocons_dist_* C ABI and every kernel behind
+    it - compiled for the host by tests/host_emul and executed on the CPU, the panels travelling over gloo
+(on a GPU the same driver runs over NCCL: tests/test_gpu_dist.py, bench.py --gpus N)."""
 import json
 import os
 import sys
@@ -134,6 +137,25 @@ def main():
           "tilt": np.array([0.3, -0.2, 0.1]), "smooth": np.array([0.2, 0.3, -0.2]), "nugget": np.array([-4, 0.1, 0.1])}
     lim = [0.5, 2.5]
     res = {}
+    if os.environ.get("COCONS_MP_EMULATED"):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from host_emul import build as emul_build
+        from host_emul.panel_ops import EmulatedPanelOps
+        work = os.path.join(os.environ["COCONS_MP_EMULATED"], "rank%d" % rank)
+        os.makedirs(work, exist_ok=True)
+        lib = emul_build.build(work)[0]
+        with DistributedDenseLikelihood(locs, X, z, ops=EmulatedPanelOps(lib, locs, X, z, rank, world)) as d:
+            t = d.terms(_lib.ML, tl, lim, tl["mean"])
+            res["ml"] = [t["logdet"]] + list(t["quad"])
+            res["panels"] = [d.npanels, [d.owner(K) for K in range(d.npanels)]]
+        if rank == 0:
+            S = cov.cov_rns(tl, locs, X, lim)
+            R = rmirror.r_chol(S)
+            y = rmirror._fwd(R, z - (X @ tl["mean"])[:, None])
+            res["ml_ref"] = [float(np.sum(np.log(np.diag(R))))] + list((y * y).sum(axis=0))
+            print("RESULT " + json.dumps(res))
+        dist.destroy_process_group()
+        return
     with DistributedDenseLikelihood(locs, X, z, ops=NumpyPanelOps(locs, X, z, rank, world)) as d:
         t = d.terms(_lib.ML, tl, lim, tl["mean"])
         res["ml"] = [t["logdet"]] + list(t["quad"])

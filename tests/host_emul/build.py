@@ -1,4 +1,4 @@
-"""TEST SCAFFOLDING: compile cocons_b200/csrc/assembly.cu, taper.cu, solve.cu and chol.cu for the HOST against the emulation shim in
+"""TEST SCAFFOLDING: compile cocons_b200/csrc/assembly.cu, taper.cu, solve.cu, chol.cu and dist.cu for the HOST against the emulation shim in
 this directory and load the result with ctypes (see cuda_runtime.h here for the execution model).
 
 The only edits made to the shipped sources are mechanical: every `kernel<<<grid, block, smem, stream>>>(args);`
@@ -33,10 +33,11 @@ def _matching(text, start, open_ch, close_ch):
 def _split_top_level(s, angle=False):
     """split at the commas outside brackets (angle: template argument lists count as brackets too)"""
     parts, depth, cur = [], 0, ""
-    for ch in s:
+    for k, ch in enumerate(s):
+        arrow = ch == ">" and k > 0 and s[k - 1] == "-"  # `->` is not a bracket
         if ch in "([{" or (angle and ch == "<"):
             depth += 1
-        elif ch in ")]}" or (angle and ch == ">"):
+        elif ch in ")]}" or (angle and ch == ">" and not arrow):
             depth -= 1
         if ch == "," and depth == 0:
             parts.append(cur.strip())
@@ -147,7 +148,7 @@ def build(workdir):
     workdir = str(workdir)
     info, launches = {}, 0
     helpers = []
-    for src in ("assembly.cu", "taper.cu", "solve.cu", "chol.cu"):
+    for src in ("assembly.cu", "taper.cu", "solve.cu", "chol.cu", "dist.cu"):
         text, names = rewrite_ptx(rewrite_dynamic_shared(open(os.path.join(CSRC, src)).read()))
         text, count, barriers = rewrite_launches(text)
         info.update(barriers)
@@ -159,7 +160,7 @@ def build(workdir):
     subprocess.check_call([
         "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
         "-I" + HERE, "-I" + workdir,
-        '-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"', '-DCHOL_INC="chol_emul.inc"',
+        '-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"', '-DCHOL_INC="chol_emul.inc"', '-DDIST_INC="dist_emul.inc"', "-Wl,-Bsymbolic",
         os.path.join(HERE, "driver.cpp"), "-o", so])
     lib = ctypes.CDLL(so)
     d, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
@@ -184,5 +185,6 @@ def build(workdir):
     lib.emu_gemm_nt.restype = None
     lib.emu_tile_count.argtypes = [i32, i32, i32, i32]
     lib.emu_tile_count.restype = i64
+    lib.emu_last_error.restype = ctypes.c_char_p
     lib.ptx_helpers = sorted(helpers)
     return lib, info, launches

@@ -94,6 +94,16 @@ cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t
 }
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) {  // the emulated "device"
+  *n = 1;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  *s = nullptr;
+  return cudaSuccess;
+}
 inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) {
   *lo = 0, *hi = -1;
   return cudaSuccess;

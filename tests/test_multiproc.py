@@ -10,18 +10,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_world_size_two_matches_single_process_reference():
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", OMP_NUM_THREADS="2")
+def _run_world_of_two(port, **extra_env):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", OMP_NUM_THREADS="2",
+               **extra_env)
     procs = []
     for rank in range(2):
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_mp_worker.py")],
                                       env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
-    outs = [p.communicate(timeout=600) for p in procs]
+    outs = [p.communicate(timeout=900) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-3000:]
     line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT ")][0]
-    res = json.loads(line[len("RESULT "):])
+    return json.loads(line[len("RESULT "):])
+
+
+def test_world_size_two_with_the_shipped_dist_kernels_on_the_host(tmp_path):
+    """The block-cyclic Cholesky of ONE matrix over two ranks with the product's own csrc/dist.cu - the cocons_dist_*
+    C ABI and every kernel behind it (cyclic-slab assembly, DMMA panel factorisation, row packing, trailing updates,
+    blocked solve, local reductions), compiled for the host and run on the CPU (tests/host_emul) - driven by the
+    product's DistributedDenseLikelihood, the packed panels broadcast and the solve blocks reduced over gloo.
+    n = 1100: three panels (512, 512, 128), dealt 0, 1, 1 by the snake."""
+    res = _run_world_of_two(29541, COCONS_MP_EMULATED=str(tmp_path))
+    assert res["panels"] == [3, [0, 1, 1]]
+    assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-11, atol=0), (res["ml"], res["ml_ref"])
+
+
+def test_world_size_two_matches_single_process_reference():
+    res = _run_world_of_two(29533)
     assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-10, atol=0)
     assert np.allclose(res["profile"], res["profile_ref"], rtol=1e-9, atol=0)
     assert res["notpd"] == "NotPositiveDefinite"
