@@ -53,6 +53,35 @@ def n2ll_cases():
     return out
 
 
+@pytest.fixture(scope="session")
+def emu(tmp_path_factory):
+    """libcocons_b200.so's sources compiled for the HOST against the CUDA execution-model stand-in of tests/host_emul
+    (test scaffolding; one build per session)."""
+    from host_emul import build as emul_build
+    # read once, at the first solve: the cooperative forward substitution needs co-resident blocks, the emulation runs
+    # blocks one after another - the library's own two-kernels-per-step variant (bit-identical) takes its place
+    os.environ["COCONS_SOLVE_COOP"] = "0"
+    lib, barriers, launches = emul_build.build(tmp_path_factory.mktemp("host_emul"))
+    lib._barriers, lib._rewritten = barriers, launches
+    return lib
+
+
+@pytest.fixture
+def product_on_host(emu, monkeypatch):
+    """The product's Python layer (cocons_b200.api / _lib) bound, for the duration of ONE test, to the host build of
+    the library's own sources instead of libcocons_b200.so - so that the host orchestration of capi.cu and the kernels
+    behind it can be checked without a GPU.  Never reachable from the product: _lib.lib() itself only ever loads
+    libcocons_b200.so, which has no CPU path."""
+    from cocons_b200 import _lib
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(emu, name)
+        fn.restype, fn.argtypes = res, args
+    monkeypatch.setattr(_lib, "_lib", emu)
+    assert _lib.lib() is emu and emu.cocons_device_count() == 1
+    yield emu
+    emu.cocons_release_workspace()
+
+
 def theta_dict(theta6):
     from oracle.cov import ASPECTS
     return {k: np.array(theta6[i]) for i, k in enumerate(ASPECTS)}

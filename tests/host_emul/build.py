@@ -1,4 +1,4 @@
-"""TEST SCAFFOLDING: compile cocons_b200/csrc/assembly.cu, taper.cu, solve.cu, chol.cu and dist.cu for the HOST against the emulation shim in
+"""TEST SCAFFOLDING: compile every source of libcocons_b200.so (cocons_b200/csrc/*.cu) for the HOST against the emulation shim in
 this directory and load the result with ctypes (see cuda_runtime.h here for the execution model).
 
 The only edits made to the shipped sources are mechanical: every `kernel<<<grid, block, smem, stream>>>(args);`
@@ -72,7 +72,8 @@ def rewrite_launches(text):
             continue
         cfg_end = text.index(">>>", m.end())
         cfg = _split_top_level(text[m.end():cfg_end], angle=True)
-        assert len(cfg) == 4, "expected <<<grid, block, smem, stream>>>: %r" % (cfg,)
+        assert 2 <= len(cfg) <= 4, "expected <<<grid, block[, smem[, stream]]>>>: %r" % (cfg,)
+        cfg += ["0", "nullptr"][len(cfg) - 2:]
         args_start = cfg_end + 3
         while text[args_start].isspace():
             args_start += 1
@@ -148,7 +149,7 @@ def build(workdir):
     workdir = str(workdir)
     info, launches = {}, 0
     helpers = []
-    for src in ("assembly.cu", "taper.cu", "solve.cu", "chol.cu", "dist.cu"):
+    for src in ("assembly.cu", "taper.cu", "solve.cu", "chol.cu", "dist.cu", "capi.cu"):
         text, names = rewrite_ptx(rewrite_dynamic_shared(open(os.path.join(CSRC, src)).read()))
         text, count, barriers = rewrite_launches(text)
         info.update(barriers)
@@ -160,7 +161,7 @@ def build(workdir):
     subprocess.check_call([
         "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
         "-I" + HERE, "-I" + workdir,
-        '-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"', '-DCHOL_INC="chol_emul.inc"', '-DDIST_INC="dist_emul.inc"', "-Wl,-Bsymbolic",
+        '-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"', '-DCHOL_INC="chol_emul.inc"', '-DDIST_INC="dist_emul.inc"', '-DCAPI_INC="capi_emul.inc"', "-Wl,-Bsymbolic",
         os.path.join(HERE, "driver.cpp"), "-o", so])
     lib = ctypes.CDLL(so)
     d, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int

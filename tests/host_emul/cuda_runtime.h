@@ -23,7 +23,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -100,6 +103,34 @@ inline cudaError_t cudaGetDeviceCount(int* n) {  // the emulated "device"
   return cudaSuccess;
 }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+constexpr cudaError_t cudaErrorMemoryAllocation = 2;
+struct cudaDeviceProp {
+  int major = 10, minor = 0, multiProcessorCount = 148;  // what check_device() of capi.cu asks for
+};
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  *p = cudaDeviceProp();
+  return cudaSuccess;
+}
+template <class T>
+cudaError_t cudaMallocHost(T** p, size_t bytes) {
+  *p = static_cast<T*>(std::malloc(bytes ? bytes : 1));
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t cudaFreeHost(void* p) {
+  std::free(p);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                cudaMemcpyKind) {
+  for (size_t r = 0; r < height; ++r)
+    std::memmove(static_cast<char*>(d) + r * dpitch, static_cast<const char*>(s) + r * spitch, width);
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
+  *ms = 0.0f;
+  return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   *s = nullptr;
   return cudaSuccess;
@@ -122,12 +153,69 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
   return cudaSuccess;
 }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }  // launches are synchronous:
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }  // synchronous launches:
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // program order
 inline cudaError_t cudaLaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) {
   std::fprintf(stderr, "host emulation: cooperative launches are driven by the test harness (grid of one block)\n");
   std::abort();
 }
+
+// ---- context switch between the fibers of a block ---------------------------------------------------------------
+// x86-64: a dozen instructions (callee-saved registers + stack pointer; swapcontext() would make two signal-mask
+// system calls per switch, and an emulated factorisation makes tens of millions of switches).  Elsewhere: ucontext.
+#if defined(__x86_64__)
+extern "C" void emul_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.hidden emul_switch
+.globl emul_switch
+.type emul_switch,@function
+emul_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emul_switch,.-emul_switch
+)");
+namespace emul {
+struct Context {
+  void* sp = nullptr;
+  // a fresh context that starts in entry() on the given stack (entry must not return)
+  void prepare(char* stack, size_t size, void (*entry)()) {
+    uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + size) & ~uintptr_t(15);
+    void** p = reinterpret_cast<void**>(top - 64);  // six saved registers, the entry address, one pad slot
+    for (int k = 0; k < 6; ++k) p[k] = nullptr;
+    p[6] = reinterpret_cast<void*>(entry);
+    p[7] = nullptr;
+    sp = p;
+  }
+  static void swap(Context& from, Context& to) { emul_switch(&from.sp, to.sp); }
+};
+}  // namespace emul
+#else
+namespace emul {
+struct Context {
+  ucontext_t uc;
+  void prepare(char* stack, size_t size, void (*entry)()) {
+    getcontext(&uc);
+    uc.uc_stack.ss_sp = stack, uc.uc_stack.ss_size = size, uc.uc_link = nullptr;
+    makecontext(&uc, entry, 0);
+  }
+  static void swap(Context& from, Context& to) { swapcontext(&from.uc, &to.uc); }
+};
+}  // namespace emul
+#endif
 
 namespace emul {
 
@@ -139,7 +227,7 @@ struct ThreadCtx {
 inline ThreadCtx ctx;
 inline long launches = 0, barrier_launches = 0;
 
-// One block of a kernel with barriers: every CUDA thread is a fiber (ucontext) of the calling OS thread.  The
+// One block of a kernel with barriers: every CUDA thread is a fiber of the calling OS thread.  The
 // scheduler resumes the runnable fibers one after another; a fiber runs until it has to wait:
 //   WAIT_BLOCK  __syncthreads(): released when every live thread of the block waits there
 //   WAIT_WARP   __syncwarp() and the warp-collective instructions (mma.sync): released when every live lane of the
@@ -170,11 +258,7 @@ class FiberBlock {
       tctx_[t].in_block = true;
       state_[t] = RUNNABLE;
       ops_[t] = 0;
-      getcontext(&fibers_[t]);
-      fibers_[t].uc_stack.ss_sp = stacks_ + kStack * t;
-      fibers_[t].uc_stack.ss_size = kStack;
-      fibers_[t].uc_link = &main_;
-      makecontext(&fibers_[t], reinterpret_cast<void (*)()>(&FiberBlock::trampoline), 0);
+      fibers_[t].prepare(stacks_ + kStack * t, kStack, &FiberBlock::trampoline);
     }
     unsigned live = nt_;
     or_acc_ = 0;
@@ -206,7 +290,7 @@ class FiberBlock {
         progressed = true;
         cur_ = t;
         ctx = tctx_[t];
-        swapcontext(&main_, &fibers_[t]);
+        Context::swap(main_, fibers_[t]);
         if (state_[t] == DONE) --live;
       }
       if (!progressed && live) {
@@ -223,7 +307,7 @@ class FiberBlock {
     if (pred) or_acc_ = 1;
     const unsigned me = cur_;
     state_[me] = state;
-    swapcontext(&fibers_[me], &main_);
+    Context::swap(fibers_[me], main_);
     return or_result_;
   }
   void poll() {
@@ -251,16 +335,18 @@ class FiberBlock {
   static void trampoline() {
     FiberBlock* b = current_block_;
     b->body_(b->body_arg_);
-    b->state_[b->cur_] = DONE;  // falls back to main_ through uc_link
+    b->state_[b->cur_] = DONE;
+    Context::swap(b->fibers_[b->cur_], b->main_);  // never resumed
+    std::abort();
   }
   static inline FiberBlock* current_block_ = nullptr;
   unsigned nt_, cur_ = 0;
-  std::vector<ucontext_t> fibers_;
+  std::vector<Context> fibers_;
   std::vector<ThreadCtx> tctx_;
   std::vector<unsigned char> state_;
   std::vector<unsigned> ops_;
   std::vector<double> xa_, xb_;
-  ucontext_t main_;
+  Context main_;
   char* stacks_ = nullptr;
   void (*body_)(void*) = nullptr;
   void* body_arg_ = nullptr;
@@ -268,8 +354,13 @@ class FiberBlock {
   unsigned long long polls_ = 0;
 };
 
+// One launch at a time in the whole process: the "shared memory" statics, the thread context and the fiber scheduler
+// are global, and the product's host code may launch from several threads (DenseLikelihoodPool)
+inline std::mutex launch_lock;
+
 template <class Body>
 void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& body) {
+  std::lock_guard<std::mutex> one_at_a_time(launch_lock);
   ++launches;
   std::vector<double> smem(smem_bytes / sizeof(double) + 2);
   void* const dyn = smem.data();

@@ -17,18 +17,9 @@
 #include SOLVE_INC
 #include CHOL_INC
 #include DIST_INC  // defines the cocons_dist_* C ABI itself: this library exports it, backed by the emulated kernels
+#include CAPI_INC  // ... and the rest of the C ABI of include/cocons_b200.h (with set_error / note_launch)
 
-#include <cstdarg>
-static char g_emu_error[512];
-namespace cocons {
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  std::vsnprintf(g_emu_error, sizeof g_emu_error, fmt, ap);
-  va_end(ap);
-}
-void note_launch(int) {}
-}  // namespace cocons
+
 
 using namespace cocons;
 
@@ -45,7 +36,7 @@ void run_variant(int mode, const double* L, int64_t ld, const double* winv, doub
 
 extern "C" {
 
-const char* emu_last_error() { return g_emu_error; }
+const char* emu_last_error() { return cocons_last_error(); }
 long emu_launches() { return emul::launches; }
 long emu_barrier_launches() { return emul::barrier_launches; }
 
