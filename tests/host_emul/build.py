@@ -14,6 +14,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cocons_b200", "csrc")
+SOURCES = ("assembly.cu", "taper.cu", "solve.cu", "chol.cu", "dist.cu", "capi.cu")
 
 
 def _matching(text, start, open_ch, close_ch):
@@ -144,12 +145,9 @@ def _absolute_includes(text):
     return re.sub(r'#include\s+"([^"]+)"', fix, text)
 
 
-def build(workdir):
-    """-> (ctypes library, {kernel name: has_barrier}, number of rewritten launches)"""
-    workdir = str(workdir)
-    info, launches = {}, 0
-    helpers = []
-    for src in ("assembly.cu", "taper.cu", "solve.cu", "chol.cu", "dist.cu", "capi.cu"):
+def _rewrite_sources(workdir):
+    info, launches, helpers = {}, 0, []
+    for src in SOURCES:
         text, names = rewrite_ptx(rewrite_dynamic_shared(open(os.path.join(CSRC, src)).read()))
         text, count, barriers = rewrite_launches(text)
         info.update(barriers)
@@ -157,11 +155,37 @@ def build(workdir):
         launches += count
         with open(os.path.join(workdir, src.replace(".cu", "_emul.inc")), "w") as f:
             f.write(_absolute_includes(text))
+    return info, launches, helpers
+
+
+INC_DEFINES = ['-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"',
+               '-DCHOL_INC="chol_emul.inc"', '-DDIST_INC="dist_emul.inc"', '-DCAPI_INC="capi_emul.inc"']
+
+
+def build_racecheck(workdir):
+    """-> path of the race-check executable: the host build with every CUDA thread a ThreadSanitizer fiber
+    (racecheck_main.cpp in this directory)"""
+    workdir = str(workdir)
+    _rewrite_sources(workdir)
+    exe = os.path.join(workdir, "racecheck")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=thread",
+                           "-DCOCONS_EMUL_TSAN", "-I" + HERE, "-I" + workdir] + INC_DEFINES +
+                          [os.path.join(HERE, "racecheck_main.cpp"), "-o", exe])
+    return exe
+
+
+def build(workdir):
+    """-> (ctypes library, {kernel name: has_barrier}, number of rewritten launches)"""
+    workdir = str(workdir)
+    info, launches, helpers = _rewrite_sources(workdir)
     so = os.path.join(workdir, "libcocons_host_emul.so")
+    # COCONS_EMUL_SANITIZE=1: AddressSanitizer + UBSan over the kernels (heap = "device" memory, globals = "shared"
+    # memory; stack instrumentation off because the fibers switch stacks) - the memcheck run of tools/emul_memcheck.sh
+    san = (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "--param", "asan-stack=0", "-g",
+            "-fno-omit-frame-pointer"] if os.environ.get("COCONS_EMUL_SANITIZE") else [])
     subprocess.check_call([
-        "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
-        "-I" + HERE, "-I" + workdir,
-        '-DASSEMBLY_INC="assembly_emul.inc"', '-DTAPER_INC="taper_emul.inc"', '-DSOLVE_INC="solve_emul.inc"', '-DCHOL_INC="chol_emul.inc"', '-DDIST_INC="dist_emul.inc"', '-DCAPI_INC="capi_emul.inc"', "-Wl,-Bsymbolic",
+        "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC"] + san + [
+        "-I" + HERE, "-I" + workdir] + INC_DEFINES + ["-Wl,-Bsymbolic",
         os.path.join(HERE, "driver.cpp"), "-o", so])
     lib = ctypes.CDLL(so)
     d, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int

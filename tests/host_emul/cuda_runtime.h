@@ -30,6 +30,12 @@
 #include <utility>
 #include <vector>
 
+#ifdef COCONS_EMUL_TSAN
+#define EMUL_NO_TSAN __attribute__((no_sanitize("thread")))
+#else
+#define EMUL_NO_TSAN
+#endif
+
 #define __global__
 #define __device__
 #define __host__
@@ -192,7 +198,7 @@ namespace emul {
 struct Context {
   void* sp = nullptr;
   // a fresh context that starts in entry() on the given stack (entry must not return)
-  void prepare(char* stack, size_t size, void (*entry)()) {
+  EMUL_NO_TSAN void prepare(char* stack, size_t size, void (*entry)()) {
     uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + size) & ~uintptr_t(15);
     void** p = reinterpret_cast<void**>(top - 64);  // six saved registers, the entry address, one pad slot
     for (int k = 0; k < 6; ++k) p[k] = nullptr;
@@ -200,7 +206,7 @@ struct Context {
     p[7] = nullptr;
     sp = p;
   }
-  static void swap(Context& from, Context& to) { emul_switch(&from.sp, to.sp); }
+  EMUL_NO_TSAN static void swap(Context& from, Context& to) { emul_switch(&from.sp, to.sp); }
 };
 }  // namespace emul
 #else
@@ -227,6 +233,29 @@ struct ThreadCtx {
 inline ThreadCtx ctx;
 inline long launches = 0, barrier_launches = 0;
 
+// ---- optional race check (-DCOCONS_EMUL_TSAN, built with -fsanitize=thread: tools/emul_racecheck.sh) ---------------
+// Every CUDA thread becomes a ThreadSanitizer fiber, switched WITHOUT synchronisation, so the only happens-before
+// edges TSan sees are the ones the kernel itself establishes: __syncthreads() / __syncwarp() / mma.sync (release by
+// every arriving thread, acquire by every leaving one), mbarrier arrive / expect_tx / complete_tx (release) ->
+// successful try_wait (acquire), the __atomic builtins behind atomicAdd & co., and block / launch boundaries.  Two
+// threads of a block touching the same shared or global location without such an edge are reported as a data race -
+// what compute-sanitizer's racecheck reports on the device.  The scheduler's own bookkeeping is not instrumented.
+#ifdef COCONS_EMUL_TSAN
+extern "C" {
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void* __tsan_get_current_fiber(void);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+inline void hb_release(void* a) { __tsan_release(a); }
+inline void hb_acquire(void* a) { __tsan_acquire(a); }
+#else
+inline void hb_release(void*) {}
+inline void hb_acquire(void*) {}
+#endif
+
 // One block of a kernel with barriers: every CUDA thread is a fiber of the calling OS thread.  The
 // scheduler resumes the runnable fibers one after another; a fiber runs until it has to wait:
 //   WAIT_BLOCK  __syncthreads(): released when every live thread of the block waits there
@@ -239,26 +268,42 @@ class FiberBlock {
  public:
   enum State : unsigned char { RUNNABLE, WAIT_BLOCK, WAIT_WARP, DONE };
   static constexpr size_t kStack = 256 * 1024;
-  explicit FiberBlock(unsigned nt)
-      : nt_(nt), fibers_(nt), tctx_(nt), state_(nt, DONE), ops_(nt, 0), xa_(((nt + 31) / 32) * 64), xb_(xa_.size()) {
+  EMUL_NO_TSAN explicit FiberBlock(unsigned nt)
+      : nt_(nt), fibers_(nt), tctx_(nt), state_(nt, DONE), ops_(nt, 0), xa_(((nt + 31) / 32) * 64), xb_(xa_.size()),
+        warp_sync_((nt + 31) / 32, 0) {
     stacks_ = static_cast<char*>(std::malloc(kStack * nt));
     if (!stacks_) std::abort();
+    // raw views for the scheduler's (uninstrumented) code: std::vector's accessors are functions of their own
+    fib_ = fibers_.data(), tc_ = tctx_.data(), st_ = state_.data(), op_ = ops_.data(), ws_ = warp_sync_.data();
+    xa_p_ = xa_.data(), xb_p_ = xb_.data();
+#ifdef COCONS_EMUL_TSAN
+    tsan_main_ = __tsan_get_current_fiber();
+    tsan_.resize(nt);
+    ts_ = tsan_.data();
+    for (unsigned t = 0; t < nt; ++t) ts_[t] = __tsan_create_fiber(0);
+#endif
   }
-  ~FiberBlock() { std::free(stacks_); }
+  EMUL_NO_TSAN ~FiberBlock() {
+#ifdef COCONS_EMUL_TSAN
+    for (void* f : tsan_) __tsan_destroy_fiber(f);
+#endif
+    std::free(stacks_);
+  }
   FiberBlock(const FiberBlock&) = delete;
 
   template <class Body>
-  void run(const Body& body, dim3 bid, dim3 block, dim3 grid, void* dyn) {
+  EMUL_NO_TSAN void run(const Body& body, dim3 bid, dim3 block, dim3 grid, void* dyn) {
+    hb_release(&launch_sync_);  // what the host (and the previous block) wrote is visible to every thread of this block
     body_ = [](void* b) { (*static_cast<const Body*>(b))(); };
     body_arg_ = const_cast<Body*>(&body);
     current_block_ = this;
     for (unsigned t = 0; t < nt_; ++t) {
-      tctx_[t].tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-      tctx_[t].bid = bid, tctx_[t].bdim = block, tctx_[t].gdim = grid, tctx_[t].dyn_smem = dyn;
-      tctx_[t].in_block = true;
-      state_[t] = RUNNABLE;
-      ops_[t] = 0;
-      fibers_[t].prepare(stacks_ + kStack * t, kStack, &FiberBlock::trampoline);
+      tc_[t].tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      tc_[t].bid = bid, tc_[t].bdim = block, tc_[t].gdim = grid, tc_[t].dyn_smem = dyn;
+      tc_[t].in_block = true;
+      st_[t] = RUNNABLE;
+      op_[t] = 0;
+      fib_[t].prepare(stacks_ + kStack * t, kStack, &FiberBlock::trampoline);
     }
     unsigned live = nt_;
     or_acc_ = 0;
@@ -266,10 +311,10 @@ class FiberBlock {
       // releases
       bool all_at_block = true;
       for (unsigned t = 0; t < nt_; ++t)
-        if (state_[t] == RUNNABLE || state_[t] == WAIT_WARP) all_at_block = false;
+        if (st_[t] == RUNNABLE || st_[t] == WAIT_WARP) all_at_block = false;
       if (all_at_block) {
         for (unsigned t = 0; t < nt_; ++t)
-          if (state_[t] == WAIT_BLOCK) state_[t] = RUNNABLE;
+          if (st_[t] == WAIT_BLOCK) st_[t] = RUNNABLE;
         or_result_ = or_acc_;  // what __syncthreads_or() of the phase just completed returns
         or_acc_ = 0;
       }
@@ -277,21 +322,21 @@ class FiberBlock {
         const unsigned w1 = w0 + 32 < nt_ ? w0 + 32 : nt_;
         bool any = false, all = true;
         for (unsigned t = w0; t < w1; ++t) {
-          if (state_[t] == WAIT_WARP) any = true;
-          if (state_[t] == RUNNABLE || state_[t] == WAIT_BLOCK) all = false;
+          if (st_[t] == WAIT_WARP) any = true;
+          if (st_[t] == RUNNABLE || st_[t] == WAIT_BLOCK) all = false;
         }
         if (any && all)
           for (unsigned t = w0; t < w1; ++t)
-            if (state_[t] == WAIT_WARP) state_[t] = RUNNABLE;
+            if (st_[t] == WAIT_WARP) st_[t] = RUNNABLE;
       }
       bool progressed = false;
       for (unsigned t = 0; t < nt_; ++t) {
-        if (state_[t] != RUNNABLE) continue;
+        if (st_[t] != RUNNABLE) continue;
         progressed = true;
         cur_ = t;
-        ctx = tctx_[t];
-        Context::swap(main_, fibers_[t]);
-        if (state_[t] == DONE) --live;
+        ctx = tc_[t];
+        switch_to(t);
+        if (st_[t] == DONE) --live;
       }
       if (!progressed && live) {
         std::fprintf(stderr, "host emulation: deadlock - %u live thread(s) of block (%u,%u,%u), none runnable "
@@ -301,16 +346,21 @@ class FiberBlock {
     }
     ctx.in_block = false;
     current_block_ = nullptr;
+    hb_acquire(&launch_sync_);  // ... and what the block wrote is visible to the host and to the next block
   }
   // from a fiber: wait in `state` (WAIT_BLOCK / WAIT_WARP), or give the turn away (RUNNABLE: a polling loop)
-  int wait(State state, int pred = 0) {
+  EMUL_NO_TSAN int wait(State state, int pred = 0) {
     if (pred) or_acc_ = 1;
     const unsigned me = cur_;
-    state_[me] = state;
-    Context::swap(fibers_[me], main_);
+    void* sync = state == WAIT_BLOCK ? static_cast<void*>(&block_sync_)
+                                     : (state == WAIT_WARP ? static_cast<void*>(&ws_[me >> 5]) : nullptr);
+    if (sync) hb_release(sync);
+    st_[me] = state;
+    switch_to_main(me);
+    if (sync) hb_acquire(sync);
     return or_result_;
   }
-  void poll() {
+  EMUL_NO_TSAN void poll() {
     if (++polls_ > (1ull << 33)) {
       std::fprintf(stderr, "host emulation: a polling loop does not end\n");
       std::abort();
@@ -320,10 +370,10 @@ class FiberBlock {
   // warp-collective exchange (mma.sync operands): every lane deposits, the warp meets, every lane reads.  Two
   // slots by the parity of the lane's collective-operation count: a lane can be at most one operation ahead of
   // the slowest lane of its warp (it has to meet the warp again), so the slot being read is never overwritten
-  void exchange(double a, double b, const double*& all_a, const double*& all_b) {
-    const unsigned t = cur_, w = t >> 5, lane = t & 31, par = ops_[t]++ & 1;
-    double* sa = xa_.data() + (w * 2 + par) * 32;
-    double* sb = xb_.data() + (w * 2 + par) * 32;
+  EMUL_NO_TSAN void exchange(double a, double b, const double*& all_a, const double*& all_b) {
+    const unsigned t = cur_, w = t >> 5, lane = t & 31, par = op_[t]++ & 1;
+    double* sa = xa_p_ + (w * 2 + par) * 32;
+    double* sb = xb_p_ + (w * 2 + par) * 32;
     sa[lane] = a, sb[lane] = b;
     wait(WAIT_WARP);
     all_a = sa, all_b = sb;
@@ -332,12 +382,26 @@ class FiberBlock {
   static FiberBlock* current() { return current_block_; }
 
  private:
-  static void trampoline() {
+  EMUL_NO_TSAN static void trampoline() {
     FiberBlock* b = current_block_;
+    hb_acquire(&b->launch_sync_);
     b->body_(b->body_arg_);
-    b->state_[b->cur_] = DONE;
-    Context::swap(b->fibers_[b->cur_], b->main_);  // never resumed
+    hb_release(&b->launch_sync_);
+    b->st_[b->cur_] = DONE;
+    b->switch_to_main(b->cur_);  // never resumed
     std::abort();
+  }
+  EMUL_NO_TSAN void switch_to(unsigned t) {
+#ifdef COCONS_EMUL_TSAN
+    __tsan_switch_to_fiber(ts_[t], 1);  // 1 = no synchronisation implied by the switch
+#endif
+    Context::swap(main_, fib_[t]);
+  }
+  EMUL_NO_TSAN void switch_to_main(unsigned me) {
+#ifdef COCONS_EMUL_TSAN
+    __tsan_switch_to_fiber(tsan_main_, 1);
+#endif
+    Context::swap(fib_[me], main_);
   }
   static inline FiberBlock* current_block_ = nullptr;
   unsigned nt_, cur_ = 0;
@@ -352,6 +416,19 @@ class FiberBlock {
   void* body_arg_ = nullptr;
   int or_acc_ = 0, or_result_ = 0;
   unsigned long long polls_ = 0;
+  char block_sync_ = 0, launch_sync_ = 0;  // addresses for the happens-before annotations of the race check
+  std::vector<char> warp_sync_;
+  Context* fib_ = nullptr;
+  ThreadCtx* tc_ = nullptr;
+  unsigned char* st_ = nullptr;
+  unsigned* op_ = nullptr;
+  char* ws_ = nullptr;
+  double *xa_p_ = nullptr, *xb_p_ = nullptr;
+#ifdef COCONS_EMUL_TSAN
+  void* tsan_main_ = nullptr;
+  std::vector<void*> tsan_;
+  void** ts_ = nullptr;
+#endif
 };
 
 // One launch at a time in the whole process: the "shared memory" statics, the thread context and the fiber scheduler
@@ -362,7 +439,7 @@ template <class Body>
 void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& body) {
   std::lock_guard<std::mutex> one_at_a_time(launch_lock);
   ++launches;
-  std::vector<double> smem(smem_bytes / sizeof(double) + 2);
+  std::vector<double> smem((smem_bytes + sizeof(double) - 1) / sizeof(double));  // exactly what was asked for
   void* const dyn = smem.data();
   const unsigned nt = block.x * block.y * block.z;
   if (!has_barrier) {
@@ -458,32 +535,39 @@ struct MBar {
   uint32_t phase : 1;
 };
 static_assert(sizeof(MBar) == 8, "an mbarrier is one 64-bit word");
-inline MBar* mbar_at(uint32_t off) { return reinterpret_cast<MBar*>(static_cast<char*>(ctx.dyn_smem) + off); }
-inline void mbar_check(MBar* m) {
+EMUL_NO_TSAN inline MBar* mbar_at(uint32_t off) { return reinterpret_cast<MBar*>(static_cast<char*>(ctx.dyn_smem) + off); }
+EMUL_NO_TSAN inline void mbar_check(MBar* m) {
   if (m->pending == 0 && m->tx == 0) m->phase ^= 1, m->pending = m->expected;
 }
-inline void ptx_mbar_init(uint32_t bar, uint32_t count) {
+EMUL_NO_TSAN inline void ptx_mbar_init(uint32_t bar, uint32_t count) {
   MBar* m = mbar_at(bar);
   m->expected = m->pending = (uint16_t)count, m->tx = 0, m->phase = 0;
 }
-inline void ptx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+EMUL_NO_TSAN inline void ptx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   MBar* m = mbar_at(bar);
+  hb_release(m);
   m->tx += (int32_t)bytes, m->pending -= 1;
   mbar_check(m);
 }
-inline void ptx_mbar_arrive(uint32_t bar) {
+EMUL_NO_TSAN inline void ptx_mbar_arrive(uint32_t bar) {
   MBar* m = mbar_at(bar);
+  // COCONS_EMUL_DROP_HANDBACK=1 (self-test of the race check): pretend the consumers' arrive on the `empty` barrier
+  // orders nothing - the producer's refill of a slot then races with the reads of that slot and must be reported
+  static const bool drop = std::getenv("COCONS_EMUL_DROP_HANDBACK") != nullptr;
+  if (!drop) hb_release(m);
   m->pending -= 1;
   mbar_check(m);
 }
 inline void ptx_mbar_arrive_after(uint32_t bar, double, double, uint32_t) { ptx_mbar_arrive(bar); }
-inline void ptx_mbar_wait(uint32_t bar, uint32_t parity) {  // until the phase with this parity has completed
+EMUL_NO_TSAN inline void ptx_mbar_wait(uint32_t bar, uint32_t parity) {  // until the phase with this parity has completed
   while (mbar_at(bar)->phase == parity) emul_block()->poll();
+  hb_acquire(mbar_at(bar));
 }
 // cp.async.bulk global -> shared with complete_tx on the barrier; synchronous here
-inline void ptx_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+EMUL_NO_TSAN inline void ptx_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   std::memcpy(static_cast<char*>(ctx.dyn_smem) + dst, src, bytes);
   MBar* m = mbar_at(bar);
+  hb_release(m);
   m->tx -= (int32_t)bytes;
   mbar_check(m);
 }

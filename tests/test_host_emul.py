@@ -443,3 +443,29 @@ def test_one_objective_evaluation_by_the_shipped_kernels_on_the_host(emu):
     got = n * np.log(2 * np.pi) + 2 * logdet + G[0, 0]
     want = rmirror.neg2loglik(theta, par_pos, locs, X, lim, z, n, (0.0, 0.0, 0.0))
     assert abs(got - want) < 1e-10 * abs(want), (got, want)
+
+
+# ---- race check: every CUDA thread a ThreadSanitizer fiber ----------------------------------------------------------
+def test_race_check_of_the_shipped_kernels(tmp_path):
+    """compute-sanitizer cannot run on the GPU pool, so the kernels' intra-block synchronisation had never been
+    race-checked (round-1 review).  Here the host build runs under ThreadSanitizer with every CUDA thread a TSan fiber
+    switched WITHOUT implied synchronisation: the only happens-before edges are the kernels' own barriers, mbarrier
+    hand-overs and atomics (tests/host_emul/cuda_runtime.h).  One pass over the DMMA GEMM (bulk-copy ring with slot
+    re-use, lower-only update, in-place panel product), the blocked Cholesky, the three forward substitutions,
+    log-determinant, Gram and the pairwise assembly must be silent; a deliberately racy kernel and a mutation that
+    drops the consumers' hand-back of a ring slot must both be reported."""
+    import os
+    import subprocess
+    from host_emul import build as emul_build
+    exe = emul_build.build_racecheck(tmp_path)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
+    env.pop("COCONS_EMUL_DROP_HANDBACK", None)
+    clean = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
+    assert clean.returncode == 0 and "racecheck done" in clean.stdout, clean.stderr[-2000:]
+    assert "ThreadSanitizer" not in clean.stderr, clean.stderr[:3000]
+    racy = subprocess.run([exe, "--racy"], env=env, capture_output=True, text=True, timeout=600)
+    assert "WARNING: ThreadSanitizer: data race" in racy.stderr and "racy_kernel" in racy.stderr
+    mutated = subprocess.run([exe], env=dict(env, COCONS_EMUL_DROP_HANDBACK="1"), capture_output=True, text=True,
+                             timeout=600)
+    assert "WARNING: ThreadSanitizer: data race" in mutated.stderr
+    assert "gemm_nt_tma_kernel" in mutated.stderr and "ptx_bulk_g2s" in mutated.stderr
