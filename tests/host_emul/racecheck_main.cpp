@@ -3,7 +3,8 @@
 // (every source of libcocons_b200.so, host build) and run by tests/test_host_emul.py / tools/emul_racecheck.sh.
 // Exit status 0 and no "ThreadSanitizer" report = no two threads of a block touched the same location without a
 // barrier, an mbarrier hand-over or an atomic in between, in any of the kernels exercised below.
-//   racecheck            run every kernel family once on a small problem
+//   racecheck            run every kernel family once on a small problem, then the C ABI and the block-cyclic path
+//   racecheck --gemm     the DMMA GEMM section only
 //   racecheck --racy     a deliberately racy kernel (neighbour exchange through shared memory without a barrier):
 //                        ThreadSanitizer MUST report it - the check has teeth
 #include "driver.cpp"
@@ -58,6 +59,7 @@ int main(int argc, char** argv) {
     std::vector<double> P = random_matrix(256, 128), W = random_matrix(128, 128);
     emu_gemm_nt(1, 256, 128, 128, P.data(), 256, W.data(), 128, P.data(), 256, 0);
     std::printf("gemm ok\n");
+    if (argc > 1 && std::string(argv[1]) == "--gemm") return 0;
   }
   // 2. blocked Cholesky: tile kernel, panel steps, look-ahead driver
   {
@@ -86,6 +88,70 @@ int main(int argc, char** argv) {
     emu_cov_square(0, n, p, locs.data(), X.data(), theta6, lim, out.data());
     emu_cov_pred(n, m, p, locs.data(), lp.data(), X.data(), Xp.data(), theta6, lim, cross.data());
     std::printf("assembly ok\n");
+  }
+  // 5. the C ABI end to end on a resident context: REML objective (design columns + z as right-hand sides, Gram
+  //    algebra), kept factor -> cocoPredict reductions, marginal and conditional draws, the tapered objective
+  {
+    setenv("COCONS_SOLVE_COOP", "0", 1);  // forward_solve(): the two-kernel variant (cooperative launch needs co-resident blocks)
+    const int64_t n = 200, m = 40, p = 3;
+    std::vector<double> locs = random_matrix(n, 2), lp = random_matrix(m, 2), X = random_matrix(n, p), Xp = random_matrix(m, p);
+    std::vector<double> z = random_matrix(n, 1), eps = random_matrix(n, 2), epsm = random_matrix(m, 2);
+    for (int64_t i = 0; i < n; ++i) X[i] = 1.0;
+    for (int64_t i = 0; i < m; ++i) Xp[i] = 1.0;
+    const double theta6[18] = {0.2, 0.15, 0.1, -1.6, 0.2, -0.15, 0.1, 0.2, -0.1, 0.3, -0.2, 0.1, 0.2, 0.3, -0.2, -4, 0.1, 0.1};
+    const double lim[2] = {0.5, 2.5}, mean[3] = {0.1, 0.3, -0.2};
+    cocons_ctx* c = nullptr;
+    if (cocons_ctx_create(0, n, p, 1, locs.data(), X.data(), z.data(), nullptr, &c) != 0) return 5;
+    double logdet = 0, quad[1], ldw = 0;
+    int rank = 0;
+    if (cocons_n2ll(c, COCONS_REML, theta6, lim, nullptr, &logdet, quad, &ldw, &rank) != 0) return 6;
+    if (cocons_n2ll(c, COCONS_ML, theta6, lim, mean, &logdet, quad, &ldw, &rank) != 0) return 7;
+    if (cocons_factor(c, COCONS_PAR_DIFF, theta6, lim) != 0) return 8;
+    std::vector<double> sto(m), expl(m), draws((size_t)n * 2), cond((size_t)m * 2);
+    if (cocons_predict(c, m, lp.data(), Xp.data(), z.data(), sto.data(), expl.data()) != 0) return 9;
+    if (cocons_sim(c, 2, eps.data(), draws.data()) != 0) return 10;
+    if (cocons_sim_cond(c, m, lp.data(), Xp.data(), 2, epsm.data(), cond.data()) != 0) return 11;
+    // tapered objective on a banded pattern (diagonal + two neighbours each side), taper 1 on the diagonal
+    std::vector<int32_t> col, row(1, 1);
+    std::vector<double> tap;
+    for (int64_t i = 0; i < n; ++i) {
+      for (int64_t j = std::max<int64_t>(0, i - 2); j <= std::min<int64_t>(n - 1, i + 2); ++j)
+        col.push_back((int32_t)j + 1), tap.push_back(i == j ? 1.0 : 0.05);
+      row.push_back((int32_t)col.size() + 1);
+    }
+    if (cocons_ctx_set_taper(c, col.data(), row.data(), tap.data(), (int64_t)col.size()) != 0) return 12;
+    if (cocons_n2ll_taper(c, theta6, lim, mean, &logdet, quad) != 0) return 13;
+    cocons_ctx_destroy(c);
+    std::printf("C ABI ok\n");
+  }
+  // 6. the block-cyclic path on one rank (csrc/dist.cu): cyclic-slab assembly, panel factorisation, row packing,
+  //    trailing updates, blocked solve with the accumulator update, local reductions.  n_pad = 640: two panels
+  {
+    const int64_t n = 600, p = 3;
+    std::vector<double> locs = random_matrix(n, 2), X = random_matrix(n, p), z = random_matrix(n, 1);
+    for (int64_t i = 0; i < n; ++i) X[i] = 1.0;
+    const double theta6[18] = {0.2, 0.15, 0.1, -1.6, 0.2, -0.15, 0.1, 0.2, -0.1, 0.3, -0.2, 0.1, 0.2, 0.3, -0.2, -4, 0.1, 0.1};
+    const double lim[2] = {0.5, 2.5}, mean[3] = {0.1, 0.3, -0.2};
+    cocons_dist* d = nullptr;
+    if (cocons_dist_create(0, 0, 1, n, p, 1, locs.data(), X.data(), z.data(), nullptr, &d) != 0) return 14;
+    const int64_t np = cocons_dist_npanels(d), n_pad = cocons_dist_npad(d);
+    if (cocons_dist_assemble(d, theta6, lim, mean) != 0) return 15;
+    std::vector<double> buf((size_t)n_pad * 512);
+    for (int64_t K = 0; K < np; ++K) {
+      if (cocons_dist_factor_panel(d, K, 0) != 0) return 16;
+      if (cocons_dist_panel_elems(d, K) > 0) {
+        if (cocons_dist_pack_panel(d, K, buf.data(), 0) != 0) return 17;
+        if (cocons_dist_update(d, K, buf.data(), K + 1, np) != 0) return 18;
+      }
+    }
+    int nr = 0;
+    std::vector<double> rhs((size_t)np * 512), acc((size_t)np * 512, 0.0), Y((size_t)n_pad), out2(2), gram(1);
+    if (cocons_dist_fill_rhs(d, COCONS_ML, rhs.data(), &nr) != 0 || nr != 1) return 19;
+    for (int64_t K = 0; K < np; ++K)
+      if (cocons_dist_solve_block(d, K, rhs.data() + K * 512, acc.data() + K * 512, acc.data(), Y.data(), nr) != 0) return 20;
+    if (cocons_dist_reduce_local(d, Y.data(), nr, out2.data(), gram.data()) != 0 || out2[1] != 0.0) return 21;
+    cocons_dist_destroy(d);
+    std::printf("block-cyclic path ok\n");
   }
   std::printf("racecheck done\n");
   return 0;

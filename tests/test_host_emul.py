@@ -452,7 +452,8 @@ def test_race_check_of_the_shipped_kernels(tmp_path):
     switched WITHOUT implied synchronisation: the only happens-before edges are the kernels' own barriers, mbarrier
     hand-overs and atomics (tests/host_emul/cuda_runtime.h).  One pass over the DMMA GEMM (bulk-copy ring with slot
     re-use, lower-only update, in-place panel product), the blocked Cholesky, the three forward substitutions,
-    log-determinant, Gram and the pairwise assembly must be silent; a deliberately racy kernel and a mutation that
+    log-determinant, Gram, the pairwise assembly, then the C ABI on a resident context (REML / ML objectives, prediction,
+    marginal and conditional draws, tapered objective) and the block-cyclic path of csrc/dist.cu must be silent; a deliberately racy kernel and a mutation that
     drops the consumers' hand-back of a ring slot must both be reported."""
     import os
     import subprocess
@@ -465,7 +466,7 @@ def test_race_check_of_the_shipped_kernels(tmp_path):
     assert "ThreadSanitizer" not in clean.stderr, clean.stderr[:3000]
     racy = subprocess.run([exe, "--racy"], env=env, capture_output=True, text=True, timeout=600)
     assert "WARNING: ThreadSanitizer: data race" in racy.stderr and "racy_kernel" in racy.stderr
-    mutated = subprocess.run([exe], env=dict(env, COCONS_EMUL_DROP_HANDBACK="1"), capture_output=True, text=True,
-                             timeout=600)
+    mutated = subprocess.run([exe, "--gemm"], env=dict(env, COCONS_EMUL_DROP_HANDBACK="1"), capture_output=True,
+                             text=True, timeout=600)
     assert "WARNING: ThreadSanitizer: data race" in mutated.stderr
     assert "gemm_nt_tma_kernel" in mutated.stderr and "ptx_bulk_g2s" in mutated.stderr
