@@ -145,6 +145,13 @@ def _absolute_includes(text):
     return re.sub(r'#include\s+"([^"]+)"', fix, text)
 
 
+def _compiler_env():
+    """the compiler itself must not run under a preloaded sanitizer runtime (tools/emul_memcheck.sh preloads ASan)"""
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    return env
+
+
 def _rewrite_sources(workdir):
     info, launches, helpers = {}, 0, []
     for src in SOURCES:
@@ -170,7 +177,7 @@ def build_racecheck(workdir):
     exe = os.path.join(workdir, "racecheck")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=thread",
                            "-DCOCONS_EMUL_TSAN", "-I" + HERE, "-I" + workdir] + INC_DEFINES +
-                          [os.path.join(HERE, "racecheck_main.cpp"), "-o", exe])
+                          [os.path.join(HERE, "racecheck_main.cpp"), "-o", exe], env=_compiler_env())
     return exe
 
 
@@ -186,7 +193,7 @@ def build(workdir):
     subprocess.check_call([
         "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC"] + san + [
         "-I" + HERE, "-I" + workdir] + INC_DEFINES + ["-Wl,-Bsymbolic",
-        os.path.join(HERE, "driver.cpp"), "-o", so])
+        os.path.join(HERE, "driver.cpp"), "-o", so], env=_compiler_env())
     lib = ctypes.CDLL(so)
     d, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.emu_launches.restype = ctypes.c_long
