@@ -10,7 +10,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_world_of_two(port, **extra_env):
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _run_world_of_two(**extra_env):
+    port = _free_port()
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", OMP_NUM_THREADS="2",
                **extra_env)
     procs = []
@@ -31,13 +39,13 @@ def test_world_size_two_with_the_shipped_dist_kernels_on_the_host(tmp_path):
     blocked solve, local reductions), compiled for the host and run on the CPU (tests/host_emul) - driven by the
     product's DistributedDenseLikelihood, the packed panels broadcast and the solve blocks reduced over gloo.
     n = 1100: three panels (512, 512, 128), dealt 0, 1, 1 by the snake."""
-    res = _run_world_of_two(29541, COCONS_MP_EMULATED=str(tmp_path))
+    res = _run_world_of_two(COCONS_MP_EMULATED=str(tmp_path))
     assert res["panels"] == [3, [0, 1, 1]]
     assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-11, atol=0), (res["ml"], res["ml_ref"])
 
 
 def test_world_size_two_matches_single_process_reference():
-    res = _run_world_of_two(29533)
+    res = _run_world_of_two()
     assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-10, atol=0)
     assert np.allclose(res["profile"], res["profile_ref"], rtol=1e-9, atol=0)
     assert res["notpd"] == "NotPositiveDefinite"
