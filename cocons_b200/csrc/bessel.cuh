@@ -5,8 +5,9 @@
 // representation for 2 < x < 25, the Hankel asymptotic tail beyond (Steed /
 // Thompson-Barnett CF2, Boost's own middle-band method, is kept for nu > 6 and for
 // nu > 3 beyond x = 18), organised for SIMT execution:
-//   * the branch taken is decided on a warp vote, so that a warp whose lanes sit
-//     in the same band runs exactly one of the three bodies;
+//   * one pair per lane; the band is a function of (nu, x) only, and the sites are Morton-ordered so that the 32
+//     lanes of a warp see nearly the same x: a warp runs one body almost always (30.7 of 32 lanes active on
+//     average);
 //   * everything is expressed through e^x K_nu(x) so that the e^-Q factor is
 //     applied once, with an exactly representable argument;
 //   * 1/Gamma(nu) comes out of the same gamma1/gamma2 polynomials the Temme
