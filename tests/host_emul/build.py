@@ -218,5 +218,6 @@ def build(workdir):
     lib.emu_tile_count.argtypes = [i32, i32, i32, i32]
     lib.emu_tile_count.restype = i64
     lib.emu_last_error.restype = ctypes.c_char_p
+    lib.emu_set_concurrent_blocks.argtypes = [i32]
     lib.ptx_helpers = sorted(helpers)
     return lib, info, launches

@@ -27,6 +27,7 @@
 #include <ucontext.h>
 #endif
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -42,7 +43,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
@@ -230,7 +231,7 @@ struct ThreadCtx {
   void* dyn_smem = nullptr;  // the launch's dynamic shared memory (one block at a time)
   bool in_block = false;     // inside a block that runs on fibers (has barriers)
 };
-inline ThreadCtx ctx;
+inline thread_local ThreadCtx ctx;
 inline long launches = 0, barrier_launches = 0;
 
 // ---- optional race check (-DCOCONS_EMUL_TSAN, built with -fsanitize=thread: tools/emul_racecheck.sh) ---------------
@@ -403,7 +404,7 @@ class FiberBlock {
 #endif
     Context::swap(fib_[me], main_);
   }
-  static inline FiberBlock* current_block_ = nullptr;
+  static inline thread_local FiberBlock* current_block_ = nullptr;
   unsigned nt_, cur_ = 0;
   std::vector<Context> fibers_;
   std::vector<ThreadCtx> tctx_;
@@ -435,29 +436,45 @@ class FiberBlock {
 // are global, and the product's host code may launch from several threads (DenseLikelihoodPool)
 inline std::mutex launch_lock;
 
+// Blocks of a kernel with barriers that run AT THE SAME TIME (default 1: one after another).  With g > 1 a launch
+// spreads its blocks over g OS threads (block b on thread b mod g), each with its own fibers, "shared memory"
+// (thread_local statics) and dynamic shared memory - real, preemptive concurrency between blocks, for the kernels whose
+// blocks talk to each other through global memory (the dataflow forward substitution: tickets, front counter,
+// partial sums).  Set through emu_set_concurrent_blocks() of driver.cpp.
+inline int concurrent_blocks = 1;
+
 template <class Body>
 void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& body) {
   std::lock_guard<std::mutex> one_at_a_time(launch_lock);
   ++launches;
-  std::vector<double> smem((smem_bytes + sizeof(double) - 1) / sizeof(double));  // exactly what was asked for
-  void* const dyn = smem.data();
+  const size_t smem_doubles = (smem_bytes + sizeof(double) - 1) / sizeof(double);  // exactly what was asked for
   const unsigned nt = block.x * block.y * block.z;
+  const unsigned nblocks = grid.x * grid.y * grid.z;
+  auto block_id = [&](unsigned b) { return dim3(b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)); };
   if (!has_barrier) {
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-      for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx)
-          for (unsigned t = 0; t < nt; ++t) {
-            ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            ctx.bid = dim3(bx, by, bz), ctx.bdim = block, ctx.gdim = grid, ctx.dyn_smem = dyn, ctx.in_block = false;
-            body();
-          }
+    std::vector<double> smem(smem_doubles);
+    for (unsigned b = 0; b < nblocks; ++b)
+      for (unsigned t = 0; t < nt; ++t) {
+        ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+        ctx.bid = block_id(b), ctx.bdim = block, ctx.gdim = grid, ctx.dyn_smem = smem.data(), ctx.in_block = false;
+        body();
+      }
     return;
   }
   ++barrier_launches;
-  FiberBlock fb(nt);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) fb.run(body, dim3(bx, by, bz), block, grid, dyn);
+  const unsigned workers = (unsigned)concurrent_blocks < nblocks ? (unsigned)concurrent_blocks : nblocks;
+  auto work = [&](unsigned w, unsigned stride) {
+    std::vector<double> smem(smem_doubles);
+    FiberBlock fb(nt);
+    for (unsigned b = w; b < nblocks; b += stride) fb.run(body, block_id(b), block, grid, smem.data());
+  };
+  if (workers <= 1) {
+    work(0, 1);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < workers; ++w) pool.emplace_back(work, w, workers);
+  for (auto& th : pool) th.join();
 }
 
 }  // namespace emul
@@ -480,7 +497,9 @@ inline void __syncwarp() { emul_block()->wait(emul::FiberBlock::WAIT_WARP); }
 
 inline int __syncthreads_or(int pred) { return emul_barrier(pred); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline void __nanosleep(unsigned) {}
+inline void __nanosleep(unsigned) {
+  if (emul::concurrent_blocks > 1) std::this_thread::yield();
+}
 template <class T>
 T __ldg(const T* p) {
   return *p;

@@ -38,6 +38,12 @@ extern "C" {
 
 const char* emu_last_error() { return cocons_last_error(); }
 long emu_launches() { return emul::launches; }
+// how many blocks of a launch run at the same time (see emul::concurrent_blocks); returns the previous value
+int emu_set_concurrent_blocks(int g) {
+  const int old = emul::concurrent_blocks;
+  emul::concurrent_blocks = g < 1 ? 1 : (g > 64 ? 64 : g);
+  return old;
+}
 long emu_barrier_launches() { return emul::barrier_launches; }
 
 int emu_cov_square(int par, int64_t n, int64_t p, const double* locs, const double* X, const double* theta6,

@@ -320,6 +320,24 @@ def test_forward_substitution_kernels_on_the_host(emu, T, nrhs):
     assert np.array_equal(got[0], _emu_solve(emu, n_pad, L, winv, B, 0))
 
 
+@pytest.mark.parametrize("T,nrhs,blocks", [(18, 1, 4), (35, 3, 8), (35, 11, 3)])
+def test_dataflow_substitution_with_truly_concurrent_blocks(emu, T, nrhs, blocks):
+    """K6b's blocks talk to each other through global memory only: a ticket counter, the front of finished tile rows,
+    per-row counters of partial sums, and y itself read through an 'unset' bit pattern.  Here several blocks run AT
+    THE SAME TIME on OS threads (pre-emptive scheduling, every interleaving the kernel is exposed to), and the result
+    must be, bit for bit, the one a single block computes alone - "results do not depend on the schedule"
+    (csrc/solve.cu) - without a stalled wait (the kernel reports one through its error word instead of hanging)."""
+    n_pad, L, winv = _factor_problem(T, 300 + T)
+    B = np.random.default_rng(T + nrhs).standard_normal((n_pad, nrhs))
+    alone = _emu_solve(emu, n_pad, L, winv, B, 0)
+    old = emu.emu_set_concurrent_blocks(blocks)
+    try:
+        for _ in range(4):
+            assert np.array_equal(_emu_solve(emu, n_pad, L, winv, B, 0), alone)
+    finally:
+        emu.emu_set_concurrent_blocks(old)
+
+
 def test_logdet_and_gram_kernels_on_the_host(emu):
     n_pad, L, _ = _factor_problem(5, 9)
     n = n_pad - 37
