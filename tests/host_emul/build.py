@@ -175,7 +175,7 @@ def build_racecheck(workdir):
     workdir = str(workdir)
     _rewrite_sources(workdir)
     exe = os.path.join(workdir, "racecheck")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=thread",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=thread", "-Wno-tsan",
                            "-DCOCONS_EMUL_TSAN", "-I" + HERE, "-I" + workdir] + INC_DEFINES +
                           [os.path.join(HERE, "racecheck_main.cpp"), "-o", exe], env=_compiler_env())
     return exe

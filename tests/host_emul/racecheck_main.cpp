@@ -4,6 +4,7 @@
 // Exit status 0 and no "ThreadSanitizer" report = no two threads of a block touched the same location without a
 // barrier, an mbarrier hand-over or an atomic in between, in any of the kernels exercised below.
 //   racecheck            run every kernel family once on a small problem, then the C ABI and the block-cyclic path
+//   racecheck --quick    smaller problems, without the block-cyclic path (what the CPU test suite runs)
 //   racecheck --gemm     the DMMA GEMM section only
 //   racecheck --racy     a deliberately racy kernel (neighbour exchange through shared memory without a barrier):
 //                        ThreadSanitizer MUST report it - the check has teeth
@@ -43,6 +44,7 @@ __global__ void racy_kernel(double* out) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  const bool quick = argc > 1 && std::string(argv[1]) == "--quick";
   if (argc > 1 && std::string(argv[1]) == "--racy") {
     std::vector<double> out(64);
     double* o = out.data();
@@ -63,7 +65,7 @@ int main(int argc, char** argv) {
   }
   // 2. blocked Cholesky: tile kernel, panel steps, look-ahead driver
   {
-    const int64_t n = 384;
+    const int64_t n = quick ? 256 : 384;
     std::vector<double> S = spd(n), W((size_t)3 * 128 * 128);
     if (emu_chol_factor(n, S.data(), W.data()) != 0) return 2;
     // 3. forward substitution on that factor: dataflow kernel, two-kernel path, cooperative kernel; logdet; Gram
@@ -93,7 +95,7 @@ int main(int argc, char** argv) {
   //    algebra), kept factor -> cocoPredict reductions, marginal and conditional draws, the tapered objective
   {
     setenv("COCONS_SOLVE_COOP", "0", 1);  // forward_solve(): the two-kernel variant (cooperative launch needs co-resident blocks)
-    const int64_t n = 200, m = 40, p = 3;
+    const int64_t n = quick ? 130 : 200, m = 40, p = 3;
     std::vector<double> locs = random_matrix(n, 2), lp = random_matrix(m, 2), X = random_matrix(n, p), Xp = random_matrix(m, p);
     std::vector<double> z = random_matrix(n, 1), eps = random_matrix(n, 2), epsm = random_matrix(m, 2);
     for (int64_t i = 0; i < n; ++i) X[i] = 1.0;
@@ -123,6 +125,10 @@ int main(int argc, char** argv) {
     if (cocons_n2ll_taper(c, theta6, lim, mean, &logdet, quad) != 0) return 13;
     cocons_ctx_destroy(c);
     std::printf("C ABI ok\n");
+  }
+  if (quick) {
+    std::printf("racecheck done\n");
+    return 0;
   }
   // 6. the block-cyclic path on one rank (csrc/dist.cu): cyclic-slab assembly, panel factorisation, row packing,
   //    trailing updates, blocked solve with the accumulator update, local reductions.  n_pad = 640: two panels
