@@ -1,19 +1,23 @@
-// TEST SCAFFOLDING - a stand-in for <cuda_runtime.h> that lets g++ compile the pairwise-assembly kernels
-// (cocons_b200/csrc/assembly.cu, taper.cu, bessel.cuh) and RUN them on the host, thread for thread, so the
-// `-m "not gpu"` suite can check the very kernel source that ships - its arithmetic order, the staging through
-// shared memory, tile / slab / slice index math - against the reference-made goldens without a device
-// (tests/test_host_emul.py).  Nothing under cocons_b200/ includes or links this; the product library has no
-// CPU path (every computing entry returns COCONS_ERR_NO_DEVICE without an sm_100 device).
+// TEST SCAFFOLDING - a stand-in for <cuda_runtime.h> that lets g++ compile EVERY source of libcocons_b200.so
+// (cocons_b200/csrc/*.cu, bessel.cuh) and RUN the kernels on the host, thread for thread, so the `-m "not gpu"` suite
+// can check the very source that ships - arithmetic order, staging through shared memory, tile / slab / slice index
+// math, the mbarrier / bulk-copy pipeline of the DMMA GEMM, the dataflow solve, the host orchestration of the C ABI -
+// against the reference-made goldens without a device, and so that the ordinary sanitizers can look at the kernels
+// (tools/emul_memcheck.sh, tools/emul_racecheck.sh).  Nothing under cocons_b200/ includes or links this; the product
+// library has no CPU path (every computing entry returns COCONS_ERR_NO_DEVICE without an sm_100 device).
 //
 // Model: a kernel launch `k<<<grid, block, smem, st>>>(args)` is rewritten by the test (tests/host_emul/build.py)
 // into emul::launch(grid, block, has_barrier, smem, [&] { k(args); }); `extern __shared__ T name[];` becomes a
-// pointer to the launch's dynamic shared memory.  Blocks run one after another.  A kernel
-// without __syncthreads() runs its threads one after another too; in one with barriers every CUDA thread is a
-// fiber, and one round-robin pass over the live fibers is one barrier phase (a thread that has left the kernel
-// counts as arrived, as on the hardware).  __shared__ becomes `static` (one block at a time, so one copy is what
-// a block sees).  Single OS thread, deterministic.
-// Round-to-nearest intrinsics map to the plain IEEE operation (compile with -ffp-contract=off), __fma_rn to
-// fma(); exp / sin / cos / log come from glibc, which legitimately differs from CUDA's libm by an ulp.
+// pointer to the launch's dynamic shared memory; a one-statement inline-PTX helper becomes a call to its stand-in
+// emul::ptx_<name> below.  Launches are synchronous (streams and events are no-ops: program order is execution
+// order).  Blocks run one after another (or, on request, a few at a time on OS threads).  A kernel without barriers
+// runs its threads one after another too; in one with barriers every CUDA thread is a fiber, and the scheduler knows
+// three ways of waiting - the block barrier, the warp-level rendezvous (__syncwarp, mma.sync), a polling loop - with
+// exited threads counting as arrived, as on the hardware.  __shared__ becomes a thread_local static (one block per OS
+// thread at a time, so one copy is what a block sees).  Round-to-nearest intrinsics map to the plain IEEE operation
+// (compile with -ffp-contract=off), __fma_rn to fma(); exp / sin / cos / log come from glibc, which legitimately
+// differs from CUDA's libm by an ulp.  Memory is sequentially consistent: fences are no-ops, and nothing here can say
+// anything about the device's memory model or its asynchronous proxy.
 #ifndef COCONS_TEST_CUDA_EMUL_H
 #define COCONS_TEST_CUDA_EMUL_H
 

@@ -1,15 +1,19 @@
-// TEST SCAFFOLDING - host-emulated runs of the shipped assembly kernels (see cuda_runtime.h in this directory).
-// ASSEMBLY_INC / TAPER_INC are cocons_b200/csrc/assembly.cu and taper.cu with their <<<...>>> launches rewritten
-// by tests/host_emul/build.py; everything else in them is compiled as it ships.  The functions below repeat
-// the few lines of orchestration the library's entry points put around those launches:
-//   emu_cov_square    cov_square()            cocons_b200/csrc/capi.cu  (cocons_cov_rns / cocons_cov_rns_classic)
+// TEST SCAFFOLDING - the host build of libcocons_b200.so's sources (see cuda_runtime.h in this directory).
+// *_INC are cocons_b200/csrc/{assembly,taper,solve,chol,dist,capi}.cu after the mechanical rewrites of
+// tests/host_emul/build.py (launch chevrons, dynamic shared memory, inline-PTX helpers); everything else in them is
+// compiled as it ships - including the C ABI itself (capi.cu, dist.cu), which this library therefore exports with the
+// emulated kernels behind it (fixture `product_on_host`, tests/_mp_worker.py).  The emu_* functions below give the
+// tests direct access to single launch helpers, repeating only the few lines of orchestration the library's entry
+// points put around them:
+//   emu_cov_square    cov_square()            capi.cu  (cocons_cov_rns / cocons_cov_rns_classic)
 //   emu_cov_pred      cocons_cov_rns_pred()   capi.cu
 //   emu_ctx_lower     assemble_and_factor()   capi.cu  (Morton-ordered, padded, lower triangle only)
-//   emu_dist_slabs    cocons_dist_assemble()  cocons_b200/csrc/dist.cu (one rank's column panels, both launch modes)
+//   emu_dist_slabs    cocons_dist_assemble()  dist.cu  (one rank's column panels, both launch modes)
 //   emu_taper_*       taper_entries_host() / the TS_LOWER sink of assemble_and_factor(taper = true)
-//   emu_forward_solve forward_solve_ws() / forward_solve()  cocons_b200/csrc/solve.cu (K6b dataflow kernel through the
-//                     library's own launcher; K6 cooperative kernel on a grid of one block; the two-kernel-per-step path)
-//   emu_logdet / emu_gram   launch_logdet() / launch_gram()
+//   emu_forward_solve forward_solve_ws() / forward_solve()  solve.cu (K6b dataflow kernel through the library's own
+//                     launcher; K6 cooperative kernel on a grid of one block; the two-kernel-per-step path)
+//   emu_logdet / emu_gram                     launch_logdet() / launch_gram()
+//   emu_chol_factor / emu_potrf_tile / emu_gemm_nt   chol_factor() / launch_potrf_tile() / launch_gemm_nt()  chol.cu
 #include "cuda_runtime.h"  // the emulation shim (found first through -I tests/host_emul)
 
 #include ASSEMBLY_INC
