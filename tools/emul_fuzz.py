@@ -3,7 +3,7 @@ restatement of the reference (oracle/rmirror.py): random shapes around the tile 
 (n, p, r, q, m, k), every objective, prediction, marginal and conditional draws.  Run it under the sanitizers with
 
     COCONS_EMUL_SANITIZE=1 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
-        ASAN_OPTIONS=detect_leaks=0 python tools/emul_fuzz.py [cases] [seed]
+        ASAN_OPTIONS=detect_leaks=0 python tools/emul_fuzz.py [cases] [seed] [--dist]
 
 to turn an out-of-bounds access at an odd shape into a report with the kernel's source line.  Needs no GPU; not part of
 the product."""
@@ -100,14 +100,47 @@ def one_case(rng, k):
     return not bad
 
 
+def dist_cases(rng):
+    """the block-cyclic driver (cocons_b200.distributed + csrc/dist.cu, one rank) against the resident context at
+    sizes around the 512-wide panel boundary: same logdet / quadratic forms / rank for ML, Profile and REML"""
+    from cocons_b200.distributed import DistributedDenseLikelihood
+    from host_emul.panel_ops import EmulatedPanelOps
+    ok = True
+    for n in (1, 2, 100, 129, 511, 512, 513, 640, 700):
+        p, r = int(rng.integers(1, 4)), int(rng.choice([1, 2, 5]))
+        locs = rng.uniform(-1, 1, (n, 2))
+        X = np.column_stack([np.ones(n), rng.standard_normal((n, p - 1))])
+        z = rng.standard_normal((n, r))
+        tl = {a: 0.2 * rng.standard_normal(p) for a in ("mean",) + cov.ASPECTS}
+        tl["scale"][0], tl["nugget"][0] = -1.4, -2.0
+        worst = 0.0
+        with cb.DenseLikelihood(locs, X, z) as ctx, \
+                DistributedDenseLikelihood(locs, X, z, ops=EmulatedPanelOps(_lib.lib(), locs, X, z, 0, 1)) as d:
+            kinds = [_lib.ML] + ([_lib.PROFILE, _lib.REML] if n > p + 1 else [])
+            if n > p + 1:
+                ctx.set_xbetas(X)
+                d.set_xbetas(X)
+            for kind in kinds:
+                a, b = ctx.terms(kind, tl, [0.5, 2.5], tl["mean"]), d.terms(kind, tl, [0.5, 2.5], tl["mean"])
+                worst = max(worst, abs(a["logdet"] - b["logdet"]) / max(abs(a["logdet"]), 1e-300),
+                            float(np.max(np.abs(a["quad"] - b["quad"]) / np.abs(a["quad"]))),
+                            abs(a["logdet_w"] - b["logdet_w"]), float(a["rank"] != b["rank"]))
+        print("dist  n=%3d p=%d r=%d  resident vs block-cyclic %.0e" % (n, p, r, worst), flush=True)
+        ok = ok and worst < 1e-10
+    return ok
+
+
 def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    argv = [a for a in sys.argv[1:] if a != "--dist"]
+    cases = int(argv[0]) if len(argv) > 0 else 20
+    seed = int(argv[1]) if len(argv) > 1 else 1
     bind()
     rng = np.random.default_rng(seed)
     t0, ok = time.time(), True
     for k in range(cases):
         ok = one_case(rng, k) and ok
+    if "--dist" in sys.argv:
+        ok = dist_cases(rng) and ok
     _lib.lib().cocons_release_workspace()
     print("%d cases in %.0f s: %s" % (cases, time.time() - t0, "all within tolerance" if ok else "FAILURES"))
     sys.exit(0 if ok else 1)
