@@ -6,8 +6,8 @@
 //   racecheck            run every kernel family once on a small problem, then the C ABI and the block-cyclic path
 //   racecheck --quick    smaller problems, without the block-cyclic path (what the CPU test suite runs)
 //   racecheck --gemm     the DMMA GEMM section only
-//   racecheck --racy     a deliberately racy kernel (neighbour exchange through shared memory without a barrier):
-//                        ThreadSanitizer MUST report it - the check has teeth
+//   racecheck --racy     two deliberately racy kernels (a neighbour exchange through shared memory without a barrier;
+//                        two concurrent blocks storing to one global location): ThreadSanitizer MUST report both
 #include "driver.cpp"
 
 #include <cstdio>
@@ -41,6 +41,13 @@ __global__ void racy_kernel(double* out) {
   out[threadIdx.x] = cell[(threadIdx.x + 1) % 64];
   __syncthreads();
 }
+// two blocks of one launch store to the same global location
+__global__ void racy_blocks_kernel(double* out) {
+  __shared__ double s;
+  if (threadIdx.x == 0) s = (double)blockIdx.x;
+  __syncthreads();
+  if (threadIdx.x == 1) out[0] = s;
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -49,9 +56,21 @@ int main(int argc, char** argv) {
     std::vector<double> out(64);
     double* o = out.data();
     emul::launch(dim3(1), dim3(64), true, 0, [&] { racy_kernel(o); });
-    std::printf("racy kernel done\n");
+    emu_set_concurrent_blocks(2);
+    emul::launch(dim3(2), dim3(32), true, 0, [&] { racy_blocks_kernel(o); });
+    std::printf("racy kernels done\n");
     return 0;
   }
+  // Sections 1, 2 (factorisation) and 4 run FOUR BLOCKS AT A TIME on OS threads: besides the hazards inside a block,
+  // ThreadSanitizer then sees every pair of blocks of a launch that touch the same global location (two CTAs writing
+  // one tile, a CTA reading what another one of the same launch writes).  The dataflow forward substitution is the one
+  // kernel whose blocks DO talk through global memory - by design, partly through plain stores polled with relaxed
+  // loads, which a race detector reports by definition; it keeps one block at a time here and is run with concurrent
+  // blocks, for its results, in tests/test_host_emul.py.
+  // (the mutation self-test keeps one block at a time: it looks for ONE specific pair of accesses inside a block, and
+  // ThreadSanitizer remembers only the last few accesses of a location)
+  const int many = std::getenv("COCONS_EMUL_DROP_HANDBACK") ? 1 : 4;
+  emu_set_concurrent_blocks(many);
   // 1. DMMA GEMM with the bulk-copy ring: K / 16 = 7 stages' worth of fills through 4 slots (slots are re-used),
   //    lower-only update and the in-place panel product
   {
@@ -68,6 +87,7 @@ int main(int argc, char** argv) {
     const int64_t n = quick ? 256 : 384;
     std::vector<double> S = spd(n), W((size_t)3 * 128 * 128);
     if (emu_chol_factor(n, S.data(), W.data()) != 0) return 2;
+    emu_set_concurrent_blocks(1);
     // 3. forward substitution on that factor: dataflow kernel, two-kernel path, cooperative kernel; logdet; Gram
     for (int mode = 0; mode < 3; ++mode) {
       std::vector<double> B = random_matrix(n, 4);  // 2 right-hand sides + scratch
@@ -79,6 +99,7 @@ int main(int argc, char** argv) {
     std::printf("cholesky / solves ok\n");
   }
   // 4. pairwise assembly (general Bessel branch): square with symmetrisation, cross-covariance
+  emu_set_concurrent_blocks(many);
   {
     const int64_t n = 200, m = 70, p = 3;
     std::vector<double> locs = random_matrix(n, 2), lp = random_matrix(m, 2), X = random_matrix(n, p), Xp = random_matrix(m, p);
@@ -91,6 +112,7 @@ int main(int argc, char** argv) {
     emu_cov_pred(n, m, p, locs.data(), lp.data(), X.data(), Xp.data(), theta6, lim, cross.data());
     std::printf("assembly ok\n");
   }
+  emu_set_concurrent_blocks(1);
   // 5. the C ABI end to end on a resident context: REML objective (design columns + z as right-hand sides, Gram
   //    algebra), kept factor -> cocoPredict reductions, marginal and conditional draws, the tapered objective
   {

@@ -468,7 +468,8 @@ def test_race_check_of_the_shipped_kernels(tmp_path):
     """compute-sanitizer cannot run on the GPU pool, so the kernels' intra-block synchronisation had never been
     race-checked (round-1 review).  Here the host build runs under ThreadSanitizer with every CUDA thread a TSan fiber
     switched WITHOUT implied synchronisation: the only happens-before edges are the kernels' own barriers, mbarrier
-    hand-overs and atomics (tests/host_emul/cuda_runtime.h).  One pass over the DMMA GEMM (bulk-copy ring with slot
+    hand-overs and atomics (tests/host_emul/cuda_runtime.h); GEMM, factorisation and assembly run four blocks at a time
+    on OS threads, so conflicts BETWEEN the blocks of a launch are seen as well.  One pass over the DMMA GEMM (bulk-copy ring with slot
     re-use, lower-only update, in-place panel product), the blocked Cholesky, the three forward substitutions,
     log-determinant, Gram, the pairwise assembly, then the C ABI on a resident context (REML / ML objectives, prediction,
     marginal and conditional draws, tapered objective) must be silent (tools/emul_racecheck.sh adds the block-cyclic
@@ -485,6 +486,7 @@ def test_race_check_of_the_shipped_kernels(tmp_path):
     assert "ThreadSanitizer" not in clean.stderr, clean.stderr[:3000]
     racy = subprocess.run([exe, "--racy"], env=env, capture_output=True, text=True, timeout=600)
     assert "WARNING: ThreadSanitizer: data race" in racy.stderr and "racy_kernel" in racy.stderr
+    assert "racy_blocks_kernel" in racy.stderr  # two concurrent blocks storing to one global location
     mutated = subprocess.run([exe, "--gemm"], env=dict(env, COCONS_EMUL_DROP_HANDBACK="1"), capture_output=True,
                              text=True, timeout=600)
     assert "WARNING: ThreadSanitizer: data race" in mutated.stderr
