@@ -69,25 +69,31 @@ int main(int argc, char** argv) {
   // blocks, for its results, in tests/test_host_emul.py.
   // (the mutation self-test keeps one block at a time: it looks for ONE specific pair of accesses inside a block, and
   // ThreadSanitizer remembers only the last few accesses of a location)
-  const int many = std::getenv("COCONS_EMUL_DROP_HANDBACK") ? 1 : 4;
-  emu_set_concurrent_blocks(many);
+  // Each of those sections runs twice - one block at a time, then four - because the detector keeps only the last
+  // few accesses of a location: the serial pass is the sharper one for hazards inside a block.
+  const bool mutation = std::getenv("COCONS_EMUL_DROP_HANDBACK") != nullptr;
   // 1. DMMA GEMM with the bulk-copy ring: K / 16 = 7 stages' worth of fills through 4 slots (slots are re-used),
   //    lower-only update and the in-place panel product
-  {
+  for (int many : {1, 4}) {
+    if (mutation && many > 1) break;
+    emu_set_concurrent_blocks(many);
     const int64_t M = 256, N = 256, K = 112;
     std::vector<double> A = random_matrix(M, K), C = random_matrix(M, N);
     emu_gemm_nt(0, M, N, K, A.data(), M, A.data(), M, C.data(), M, 1);
     std::vector<double> P = random_matrix(256, 128), W = random_matrix(128, 128);
     emu_gemm_nt(1, 256, 128, 128, P.data(), 256, W.data(), 128, P.data(), 256, 0);
-    std::printf("gemm ok\n");
-    if (argc > 1 && std::string(argv[1]) == "--gemm") return 0;
+    std::printf("gemm ok (%d block(s) at a time)\n", many);
   }
-  // 2. blocked Cholesky: tile kernel, panel steps, look-ahead driver
-  {
+  if (argc > 1 && std::string(argv[1]) == "--gemm") return 0;
+  // 2. blocked Cholesky: tile kernel, panel steps, look-ahead driver (quick: the concurrent pass only)
+  for (int many : {1, 4}) {
+    if (quick && many == 1) continue;
+    emu_set_concurrent_blocks(many);
     const int64_t n = quick ? 256 : 384;
     std::vector<double> S = spd(n), W((size_t)3 * 128 * 128);
     if (emu_chol_factor(n, S.data(), W.data()) != 0) return 2;
     emu_set_concurrent_blocks(1);
+    if (many == 1) continue;
     // 3. forward substitution on that factor: dataflow kernel, two-kernel path, cooperative kernel; logdet; Gram
     for (int mode = 0; mode < 3; ++mode) {
       std::vector<double> B = random_matrix(n, 4);  // 2 right-hand sides + scratch
@@ -99,8 +105,8 @@ int main(int argc, char** argv) {
     std::printf("cholesky / solves ok\n");
   }
   // 4. pairwise assembly (general Bessel branch): square with symmetrisation, cross-covariance
-  emu_set_concurrent_blocks(many);
-  {
+  for (int many : {1, 4}) {
+    emu_set_concurrent_blocks(many);
     const int64_t n = 200, m = 70, p = 3;
     std::vector<double> locs = random_matrix(n, 2), lp = random_matrix(m, 2), X = random_matrix(n, p), Xp = random_matrix(m, p);
     for (int64_t i = 0; i < n; ++i) X[i] = 1.0;
