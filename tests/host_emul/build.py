@@ -217,6 +217,8 @@ def build(workdir):
     lib.emu_gemm_nt.restype = None
     lib.emu_tile_count.argtypes = [i32, i32, i32, i32]
     lib.emu_tile_count.restype = i64
+    lib.emu_tile_decode_check.argtypes = [i32, ctypes.POINTER(ctypes.c_long)]
+    lib.emu_tile_decode_check.restype = ctypes.c_long
     lib.emu_last_error.restype = ctypes.c_char_p
     lib.emu_set_concurrent_blocks.argtypes = [i32]
     lib.ptx_helpers = sorted(helpers)

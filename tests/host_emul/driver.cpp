@@ -28,6 +28,28 @@
 using namespace cocons;
 
 namespace {
+// the exhaustive check of tools/micro/tile_decode_check.cu: total_tiles / tile_decode<W> must be a bijection onto
+// the expected tile set of an (ni x njc) update, full or lower-trapezoid
+template <int W>
+long tile_decode_errors(int ni, int njc, int lower) {
+  const int64_t total = total_tiles<W>(ni, njc, lower);
+  std::vector<unsigned char> seen((size_t)ni * njc, 0);
+  long bad = 0;
+  int64_t expect = 0;
+  for (int bi = 0; bi < ni; ++bi)
+    for (int c = 0; c < njc; ++c)
+      if (!lower || bi >= c / W) ++expect;
+  if (expect != total) return 1 + std::llabs(expect - total);
+  for (int64_t t = 0; t < total; ++t) {
+    int bi = -1, bj = -1;
+    tile_decode<W>(t, ni, njc, lower, bi, bj);
+    if (bi < 0 || bi >= ni || bj < 0 || bj >= njc || (lower && bi < bj / W) || seen[(size_t)bi * njc + bj]++) ++bad;
+  }
+  return bad;
+}
+}  // namespace
+
+namespace {
 template <int NR>
 void run_variant(int mode, const double* L, int64_t ld, const double* winv, double* B, double* Y, int64_t ldb,
                  int64_t nt, int nr) {
@@ -228,6 +250,24 @@ int emu_potrf_tile(double* A, int64_t ld, double* winv, int first_index) {
 void emu_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
                  double* C, int64_t ldc, int lower_only) {
   launch_gemm_nt(mode, M, N, K, A, lda, B, ldb, C, ldc, lower_only, nullptr);
+}
+
+// -> number of wrong decodes over *shapes shapes (0 = the numbering is a bijection everywhere)
+long emu_tile_decode_check(int ni_max, long* shapes_out) {
+  long shapes = 0, bad = 0;
+  for (int ni = 1; ni <= ni_max; ++ni) {
+    const int step = ni < 80 ? 1 : 7;
+    for (int nj = 1; nj <= ni; nj += step) {
+      bad += tile_decode_errors<1>(ni, nj, 1), bad += tile_decode_errors<2>(ni, 2 * nj, 1), shapes += 2;
+      if (nj <= 12) bad += tile_decode_errors<1>(ni, nj, 0), bad += tile_decode_errors<2>(ni, 2 * nj, 0), shapes += 2;
+    }
+    bad += tile_decode_errors<2>(ni, 2 * ni, 1), bad += tile_decode_errors<1>(ni, ni, 1), shapes += 2;
+  }
+  for (int ni : {781, 782, 1563, 1564})
+    bad += tile_decode_errors<2>(ni, 2 * ni, 1), bad += tile_decode_errors<2>(ni, 12, 1),
+        bad += tile_decode_errors<1>(ni, 1, 0), shapes += 3;
+  *shapes_out = shapes;
+  return bad;
 }
 
 int64_t emu_tile_count(int w, int ni, int njc, int lower_only) {
