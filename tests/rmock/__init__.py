@@ -35,9 +35,12 @@ class ExtPtr:
 
 
 class RMock:
-    def __init__(self, workdir, glue_source=None):
+    def __init__(self, workdir, glue_source=None, library=None):
         """glue_source: another C file registering its routines through R_init_cocons (the self-test of the checks);
-        default: the product's cocons_b200/rglue/cocons_glue.c"""
+        default: the product's cocons_b200/rglue/cocons_glue.c.
+        library: path of the shared object providing the C ABI; default libcocons_b200.so (the product).  The CPU suite
+        also links the glue against the HOST BUILD of the library's sources (tests/host_emul) to run the .Call sequences
+        end to end without a GPU."""
         workdir = str(workdir)
         alloc_h = os.path.join(workdir, "rmock_alloc.h")
         with open(alloc_h, "w") as f:
@@ -49,8 +52,11 @@ class RMock:
         subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter", "-c"] + inc +
                               ["-include", alloc_h, glue_source or os.path.join(GLUE, "cocons_glue.c"), "-o", glue_o])
         subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-c"] + inc + [os.path.join(HERE, "rmock.c"), "-o", mock_o])
-        subprocess.check_call(["gcc", "-shared", glue_o, mock_o, "-L" + LIBDIR, "-lcocons_b200",
-                               "-Wl,-rpath," + LIBDIR, "-o", so])
+        if library is None:
+            link = ["-L" + LIBDIR, "-lcocons_b200", "-Wl,-rpath," + LIBDIR]
+        else:
+            link = [library, "-Wl,-rpath," + os.path.dirname(library)]
+        subprocess.check_call(["gcc", "-shared", glue_o, mock_o] + link + ["-o", so])
         L = self.lib = ctypes.CDLL(so)
         vp, ci, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
         for name, res, args in (

@@ -5,7 +5,8 @@ out of Rf_error().  The miniature collects garbage at EVERY allocation, checks t
 the glue's malloc / free - what gctorture / valgrind would check under real R, which this image does not have.
 
 CPU tests: registration table (src/RcppExports.cpp:105-118), argument handling (lookup by name, coercion, shape
-errors raised before a device is touched), the one host-only routine end to end, no CPU fallback.
+errors raised before a device is touched), the one host-only routine end to end, no CPU fallback; and the GPU tests'
+.Call sequences with the glue linked against the HOST BUILD of the library's sources (tests/host_emul).
 GPU tests (-m gpu): the same calls an R session would make, against the reference-made goldens."""
 import numpy as np
 import pytest
@@ -153,6 +154,27 @@ void R_init_cocons(DllInfo* dll) { R_registerRoutines(dll, NULL, entries, NULL, 
     assert r.call("bad_leak", 0) is None
     assert np.array_equal(r.call("good", 1), np.array([[1.0, 2.0]]))
     r.release_all()
+
+
+# ---- the same .Call sequences on the CPU: the glue linked against the HOST BUILD of the library (tests/host_emul) -----
+@pytest.fixture(scope="module")
+def R_host(tmp_path_factory, emu):
+    r = RMock(tmp_path_factory.mktemp("rmock_host"), library=emu._name)
+    yield r
+    r.release_all()
+
+
+def test_dot_call_sequences_end_to_end_on_the_host_build(R_host, cov_cases, taper_cases, n2ll_cases, datasets):
+    """R object -> glue -> C ABI -> kernels -> R object, every layer executed (the kernels by the host emulation):
+    the GPU tests below, at the sizes the emulation finishes in seconds"""
+    test_cov_entry_points_through_dot_call_match_the_goldens(R_host, cov_cases)
+    test_taper_entry_points_through_dot_call_match_the_goldens(R_host, taper_cases)
+    test_not_positive_definite_is_a_status_not_an_r_error(R_host, n2ll_cases, datasets)
+    test_objectives_through_dot_call_match_the_goldens(R_host, "holes777_ragged", n2ll_cases, datasets)
+
+
+def test_context_lifecycle_on_the_host_build(R_host, product_on_host, n2ll_cases, datasets):
+    test_context_lifecycle_through_dot_call(R_host, n2ll_cases, datasets)
 
 
 # ---- GPU: what an R session would call --------------------------------------------------------------------------------
