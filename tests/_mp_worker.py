@@ -147,12 +147,19 @@ def main():
         with DistributedDenseLikelihood(locs, X, z, ops=EmulatedPanelOps(lib, locs, X, z, rank, world)) as d:
             t = d.terms(_lib.ML, tl, lim, tl["mean"])
             res["ml"] = [t["logdet"]] + list(t["quad"])
+            t = d.terms(_lib.REML, tl, lim)  # p design columns + r columns of z as right-hand sides, Gram algebra, rank
+            res["reml"] = [t["logdet"], t["logdet_w"], float(t["rank"])] + list(t["quad"])
             res["panels"] = [d.npanels, [d.owner(K) for K in range(d.npanels)]]
         if rank == 0:
             S = cov.cov_rns(tl, locs, X, lim)
             R = rmirror.r_chol(S)
             y = rmirror._fwd(R, z - (X @ tl["mean"])[:, None])
             res["ml_ref"] = [float(np.sum(np.log(np.diag(R))))] + list((y * y).sum(axis=0))
+            Yx, yz = rmirror._fwd(R, X), rmirror._fwd(R, z)
+            W, b = Yx.T @ Yx, Yx.T @ yz
+            quad = (yz * yz).sum(axis=0) - np.einsum("ij,ij->j", b, np.linalg.solve(W, b))
+            res["reml_ref"] = [float(np.sum(np.log(np.diag(R)))), float(np.sum(np.log(np.diag(np.linalg.cholesky(W))))),
+                               float(rmirror.r_qr_rank(X))] + list(quad)
             print("RESULT " + json.dumps(res))
         dist.destroy_process_group()
         return

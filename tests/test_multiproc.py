@@ -42,6 +42,7 @@ def test_world_size_two_with_the_shipped_dist_kernels_on_the_host(tmp_path):
     res = _run_world_of_two(COCONS_MP_EMULATED=str(tmp_path))
     assert res["panels"] == [3, [0, 1, 1]]
     assert np.allclose(res["ml"], res["ml_ref"], rtol=1e-11, atol=0), (res["ml"], res["ml_ref"])
+    assert np.allclose(res["reml"], res["reml_ref"], rtol=1e-10, atol=0), (res["reml"], res["reml_ref"])
 
 
 def test_world_size_two_matches_single_process_reference():
