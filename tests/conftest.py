@@ -58,9 +58,6 @@ def emu(tmp_path_factory):
     """libcocons_b200.so's sources compiled for the HOST against the CUDA execution-model stand-in of tests/host_emul
     (test scaffolding; one build per session)."""
     from host_emul import build as emul_build
-    # read once, at the first solve: the cooperative forward substitution needs co-resident blocks, the emulation runs
-    # blocks one after another - the library's own two-kernels-per-step variant (bit-identical) takes its place
-    os.environ["COCONS_SOLVE_COOP"] = "0"
     lib, barriers, launches = emul_build.build(tmp_path_factory.mktemp("host_emul"))
     lib._barriers, lib._rewritten = barriers, launches
     return lib

@@ -4,7 +4,8 @@ this directory and load the result with ctypes (see cuda_runtime.h here for the 
 The only edits made to the shipped sources are mechanical: every `kernel<<<grid, block, smem, stream>>>(args);`
 becomes `emul::launch(grid, block, has_barrier, smem, [&] { kernel(args); });` (g++ cannot parse the chevrons), where
 has_barrier says whether the kernel's body contains a barrier; `extern __shared__ T x[];` becomes a pointer to the
-launch's dynamic shared memory; inline PTX is handled by the two rules of rewrite_ptx(); `#include "x"` lines are made
+launch's dynamic shared memory; inline PTX is handled by the two rules of rewrite_ptx(); a cooperative launch becomes
+a launch of ONE block (rewrite_cooperative_launches()); `#include "x"` lines are made
 absolute because the rewritten text is compiled from a scratch directory."""
 import ctypes
 import os
@@ -89,6 +90,25 @@ def rewrite_launches(text):
     return out + text[pos:], count, barriers
 
 
+def rewrite_cooperative_launches(text):
+    """`void* args[] = {(void*)&a, (void*)&b, ...}; ... cudaLaunchCooperativeKernel((void*)k<T>, grid, block, args, smem,
+    st);` -> the kernel on a grid of ONE block (blocks run one after another here, and a cooperative kernel needs all
+    of its blocks resident: with one block grid.sync() is the block barrier; the kernels stride over gridDim.x, so any
+    grid size computes the same thing)."""
+    out, pos = "", 0
+    for m in re.finditer(r"cudaLaunchCooperativeKernel\s*\(", text):
+        end = _matching(text, m.end() - 1, "(", ")")
+        parts = _split_top_level(text[m.end():end - 1], angle=True)
+        assert len(parts) == 6, parts
+        kernel = re.sub(r"^\(void\s*\*\)\s*", "", parts[0])
+        decl = list(re.finditer(r"void\s*\*\s*%s\s*\[\]\s*=\s*\{([^}]*)\}" % re.escape(parts[3]), text[:m.start()]))[-1]
+        names = [re.sub(r"^\(void\s*\*\)\s*&\s*", "", a.strip()) for a in decl.group(1).split(",")]
+        out += text[pos:m.start()] + "emul::launch(dim3(1), %s, true, %s, [&] { %s(%s); })" % (
+            parts[2], parts[4], kernel, ", ".join(names))
+        pos = end
+    return out + text[pos:]
+
+
 def rewrite_dynamic_shared(text):
     """`extern __shared__ [__align__(n)] T name[];` -> a pointer to the launch's dynamic shared memory"""
     return re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];",
@@ -155,7 +175,8 @@ def _compiler_env():
 def _rewrite_sources(workdir):
     info, launches, helpers = {}, 0, []
     for src in SOURCES:
-        text, names = rewrite_ptx(rewrite_dynamic_shared(open(os.path.join(CSRC, src)).read()))
+        text, names = rewrite_ptx(rewrite_dynamic_shared(rewrite_cooperative_launches(
+            open(os.path.join(CSRC, src)).read())))
         text, count, barriers = rewrite_launches(text)
         info.update(barriers)
         helpers += names

@@ -167,7 +167,7 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }  // synchronous launches:
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // program order
 inline cudaError_t cudaLaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) {
-  std::fprintf(stderr, "host emulation: cooperative launches are driven by the test harness (grid of one block)\n");
+  std::fprintf(stderr, "host emulation: cooperative launches are rewritten by build.py (grid of one block)\n");
   std::abort();
 }
 

@@ -4,7 +4,6 @@ kernels (cyclic-slab assembly, blocked Cholesky of the owned panels, row packing
 solve, local reductions), executed on the CPU; the exchanged buffers are CPU torch tensors, so the driver's
 broadcasts / reduces run over gloo.  Mirrors CudaPanelOps call for call (one queue: no side stream)."""
 import ctypes
-import os
 
 import torch
 
@@ -14,10 +13,6 @@ from cocons_b200.distributed import _NoSync
 
 class EmulatedPanelOps(_NoSync):
     def __init__(self, lib, locs, X, z, rank, world):
-        # the blocked solve of a panel goes through forward_solve(): its cooperative launch needs every CTA resident at
-        # once, which sequential blocks cannot give - the library's own two-kernels-per-step variant (same arithmetic,
-        # bit-identical results: tests/test_host_emul.py) is selected instead
-        os.environ["COCONS_SOLVE_COOP"] = "0"
         self.lib = lib
         for name, (res, args) in _lib.SIGNATURES.items():
             if name.startswith("cocons_dist_"):

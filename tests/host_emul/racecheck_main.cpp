@@ -122,7 +122,6 @@ int main(int argc, char** argv) {
   // 5. the C ABI end to end on a resident context: REML objective (design columns + z as right-hand sides, Gram
   //    algebra), kept factor -> cocoPredict reductions, marginal and conditional draws, the tapered objective
   {
-    setenv("COCONS_SOLVE_COOP", "0", 1);  // forward_solve(): the two-kernel variant (cooperative launch needs co-resident blocks)
     const int64_t n = quick ? 130 : 200, m = 40, p = 3;
     std::vector<double> locs = random_matrix(n, 2), lp = random_matrix(m, 2), X = random_matrix(n, p), Xp = random_matrix(m, p);
     std::vector<double> z = random_matrix(n, 1), eps = random_matrix(n, 2), epsm = random_matrix(m, 2);

@@ -17,7 +17,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["COCONS_SOLVE_COOP"] = "0"
 
 import cocons_b200 as cb  # noqa: E402
 from cocons_b200 import _lib  # noqa: E402
