@@ -47,16 +47,21 @@ class RMock:
             f.write("#include <stdlib.h>\nvoid* rmock_malloc(size_t);\nvoid rmock_free(void*);\n"
                     "#define malloc rmock_malloc\n#define free rmock_free\n")
         inc = ["-I" + os.path.join(GLUE, "stub")]
+        if os.environ.get("COCONS_EMUL_SANITIZE"):  # tools/emul_memcheck.sh: the glue's marshalling under ASan + UBSan
+            inc += ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
+        env = dict(os.environ)
+        env.pop("LD_PRELOAD", None)  # the compiler itself does not run under the preloaded sanitizer runtime
         glue_o, mock_o = os.path.join(workdir, "glue.o"), os.path.join(workdir, "rmock.o")
         so = os.path.join(workdir, "cocons_rmock.so")
         subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter", "-c"] + inc +
-                              ["-include", alloc_h, glue_source or os.path.join(GLUE, "cocons_glue.c"), "-o", glue_o])
-        subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-c"] + inc + [os.path.join(HERE, "rmock.c"), "-o", mock_o])
+                              ["-include", alloc_h, glue_source or os.path.join(GLUE, "cocons_glue.c"), "-o", glue_o], env=env)
+        subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-c"] + inc + [os.path.join(HERE, "rmock.c"), "-o", mock_o],
+                              env=env)
         if library is None:
             link = ["-L" + LIBDIR, "-lcocons_b200", "-Wl,-rpath," + LIBDIR]
         else:
             link = [library, "-Wl,-rpath," + os.path.dirname(library)]
-        subprocess.check_call(["gcc", "-shared", glue_o, mock_o] + link + ["-o", so])
+        subprocess.check_call(["gcc", "-shared", glue_o, mock_o] + link + ["-o", so], env=env)
         L = self.lib = ctypes.CDLL(so)
         vp, ci, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
         for name, res, args in (
