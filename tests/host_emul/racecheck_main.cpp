@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <random>
+#include <thread>
 
 namespace {
 std::mt19937_64 rng(20261018);
@@ -185,6 +186,33 @@ int main(int argc, char** argv) {
     if (cocons_dist_reduce_local(d, Y.data(), nr, out2.data(), gram.data()) != 0 || out2[1] != 0.0) return 21;
     cocons_dist_destroy(d);
     std::printf("block-cyclic path ok\n");
+  }
+  // 7. several host threads, each driving its own context (DenseLikelihoodPool; INTEGRATION.md "several host threads
+  //    may drive several contexts on one device"): the library's host-side state - error buffer, launch counter,
+  //    per-context streams / workspaces / staging buffers - must not be shared between them without synchronisation
+  {
+    const int64_t n = 130, p = 3;
+    std::vector<double> locs = random_matrix(n, 2), X = random_matrix(n, p), z = random_matrix(n, 1);
+    for (int64_t i = 0; i < n; ++i) X[i] = 1.0;
+    const double theta6[18] = {0.2, 0.15, 0.1, -1.6, 0.2, -0.15, 0.1, 0.2, -0.1, 0.3, -0.2, 0.1, 0.2, 0.3, -0.2, -4, 0.1, 0.1};
+    const double lim[2] = {0.5, 2.5}, mean[3] = {0.1, 0.3, -0.2};
+    double values[3] = {0, 0, 0};
+    int status[3] = {0, 0, 0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < 3; ++t)
+      pool.emplace_back([&, t] {
+        cocons_ctx* c = nullptr;
+        double quad[1], ldw = 0;
+        int rank = 0;
+        status[t] = cocons_ctx_create(0, n, p, 1, locs.data(), X.data(), z.data(), nullptr, &c);
+        for (int rep = 0; rep < 2 && status[t] == 0; ++rep)
+          status[t] = cocons_n2ll(c, COCONS_ML, theta6, lim, mean, &values[t], quad, &ldw, &rank);
+        if (c) cocons_ctx_destroy(c);
+      });
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < 3; ++t)
+      if (status[t] != 0 || values[t] != values[0]) return 22;
+    std::printf("host threads ok\n");
   }
   std::printf("racecheck done\n");
   return 0;
