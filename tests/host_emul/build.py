@@ -234,6 +234,7 @@ def build(workdir):
     lib.emu_gram.restype = None
     lib.emu_chol_factor.argtypes = [i64, d, d]
     lib.emu_potrf_tile.argtypes = [d, i64, d, i32]
+    lib.emu_potrf_tile_sweep.argtypes = [d, i64, d, i32]
     lib.emu_gemm_nt.argtypes = [i32, i64, i64, i64, d, i64, d, i64, d, i64, i32]
     lib.emu_gemm_nt.restype = None
     lib.emu_tile_count.argtypes = [i32, i32, i32, i32]

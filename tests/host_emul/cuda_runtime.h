@@ -233,6 +233,7 @@ namespace emul {
 struct ThreadCtx {
   dim3 tid, bid, bdim, gdim;
   void* dyn_smem = nullptr;  // the launch's dynamic shared memory (one block at a time)
+  size_t dyn_bytes = 0;
   bool in_block = false;     // inside a block that runs on fibers (has barriers)
 };
 inline thread_local ThreadCtx ctx;
@@ -264,8 +265,8 @@ inline void hb_acquire(void*) {}
 // One block of a kernel with barriers: every CUDA thread is a fiber of the calling OS thread.  The
 // scheduler resumes the runnable fibers one after another; a fiber runs until it has to wait:
 //   WAIT_BLOCK  __syncthreads(): released when every live thread of the block waits there
-//   WAIT_WARP   __syncwarp() and the warp-collective instructions (mma.sync): released when every live lane of the
-//               warp waits there
+//   WAIT_WARP   __syncwarp(), the warp-collective mma.sync and __shfl_sync(mask, ...): released when every live lane
+//               named in the mask waits there with the same mask
 //   (RUNNABLE)  a polling loop (mbarrier.try_wait) gives the turn away and is resumed in the next pass
 // A thread that has left the kernel counts as arrived, as on the hardware.  Nothing runnable while threads are
 // alive is a deadlock and ends the test with a message.  Deterministic; a barrier costs `block` context switches.
@@ -275,12 +276,13 @@ class FiberBlock {
   static constexpr size_t kStack = 256 * 1024;
   EMUL_NO_TSAN explicit FiberBlock(unsigned nt)
       : nt_(nt), fibers_(nt), tctx_(nt), state_(nt, DONE), ops_(nt, 0), xa_(((nt + 31) / 32) * 64), xb_(xa_.size()),
-        warp_sync_((nt + 31) / 32, 0) {
+        warp_sync_((nt + 31) / 32, 0), wmask_(nt, 0), shc_(nt, 0), shv_(2 * (size_t)nt, 0.0) {
     stacks_ = static_cast<char*>(std::malloc(kStack * nt));
     if (!stacks_) std::abort();
     // raw views for the scheduler's (uninstrumented) code: std::vector's accessors are functions of their own
     fib_ = fibers_.data(), tc_ = tctx_.data(), st_ = state_.data(), op_ = ops_.data(), ws_ = warp_sync_.data();
     xa_p_ = xa_.data(), xb_p_ = xb_.data();
+    wm_ = wmask_.data(), sc_ = shc_.data(), sv_ = shv_.data();
 #ifdef COCONS_EMUL_TSAN
     tsan_main_ = __tsan_get_current_fiber();
     tsan_.resize(nt);
@@ -297,7 +299,7 @@ class FiberBlock {
   FiberBlock(const FiberBlock&) = delete;
 
   template <class Body>
-  EMUL_NO_TSAN void run(const Body& body, dim3 bid, dim3 block, dim3 grid, void* dyn) {
+  EMUL_NO_TSAN void run(const Body& body, dim3 bid, dim3 block, dim3 grid, void* dyn, size_t dyn_bytes) {
     hb_release(&launch_sync_);  // what the host (and the previous block) wrote is visible to every thread of this block
     body_ = [](void* b) { (*static_cast<const Body*>(b))(); };
     body_arg_ = const_cast<Body*>(&body);
@@ -305,9 +307,10 @@ class FiberBlock {
     for (unsigned t = 0; t < nt_; ++t) {
       tc_[t].tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
       tc_[t].bid = bid, tc_[t].bdim = block, tc_[t].gdim = grid, tc_[t].dyn_smem = dyn;
+      tc_[t].dyn_bytes = dyn_bytes;
       tc_[t].in_block = true;
       st_[t] = RUNNABLE;
-      op_[t] = 0;
+      op_[t] = 0, sc_[t] = 0;
       fib_[t].prepare(stacks_ + kStack * t, kStack, &FiberBlock::trampoline);
     }
     unsigned live = nt_;
@@ -325,14 +328,16 @@ class FiberBlock {
       }
       for (unsigned w0 = 0; w0 < nt_; w0 += 32) {
         const unsigned w1 = w0 + 32 < nt_ ? w0 + 32 : nt_;
-        bool any = false, all = true;
         for (unsigned t = w0; t < w1; ++t) {
-          if (st_[t] == WAIT_WARP) any = true;
-          if (st_[t] == RUNNABLE || st_[t] == WAIT_BLOCK) all = false;
+          if (st_[t] != WAIT_WARP) continue;
+          const unsigned mask = wm_[t];
+          bool all = true;  // every live lane named in the mask waits with this very mask
+          for (unsigned l = w0; l < w1 && all; ++l)
+            if (((mask >> (l - w0)) & 1u) && st_[l] != DONE && !(st_[l] == WAIT_WARP && wm_[l] == mask)) all = false;
+          if (all)
+            for (unsigned l = w0; l < w1; ++l)
+              if (((mask >> (l - w0)) & 1u) && st_[l] == WAIT_WARP) st_[l] = RUNNABLE;
         }
-        if (any && all)
-          for (unsigned t = w0; t < w1; ++t)
-            if (st_[t] == WAIT_WARP) st_[t] = RUNNABLE;
       }
       bool progressed = false;
       for (unsigned t = 0; t < nt_; ++t) {
@@ -354,9 +359,10 @@ class FiberBlock {
     hb_acquire(&launch_sync_);  // ... and what the block wrote is visible to the host and to the next block
   }
   // from a fiber: wait in `state` (WAIT_BLOCK / WAIT_WARP), or give the turn away (RUNNABLE: a polling loop)
-  EMUL_NO_TSAN int wait(State state, int pred = 0) {
+  EMUL_NO_TSAN int wait(State state, int pred = 0, unsigned mask = 0xFFFFFFFFu) {
     if (pred) or_acc_ = 1;
     const unsigned me = cur_;
+    wm_[me] = mask;
     void* sync = state == WAIT_BLOCK ? static_cast<void*>(&block_sync_)
                                      : (state == WAIT_WARP ? static_cast<void*>(&ws_[me >> 5]) : nullptr);
     if (sync) hb_release(sync);
@@ -382,6 +388,15 @@ class FiberBlock {
     sa[lane] = a, sb[lane] = b;
     wait(WAIT_WARP);
     all_a = sa, all_b = sb;
+  }
+  // __shfl_sync(mask, v, src): the lanes of the mask meet; each reads lane src's deposit.  The lanes of a mask group
+  // are assumed to have done the same number of shuffles (they shuffle together), which makes the reader's parity the
+  // writer's; a lane can run at most one shuffle ahead of its group, into the other slot
+  EMUL_NO_TSAN double shuffle(unsigned mask, double v, int src) {
+    const unsigned t = cur_, w0 = t & ~31u, par = sc_[t]++ & 1;
+    sv_[2 * t + par] = v;
+    wait(WAIT_WARP, 0, mask);
+    return sv_[2 * (w0 + (unsigned)(src & 31)) + par];
   }
   unsigned lane() const { return cur_ & 31; }
   static FiberBlock* current() { return current_block_; }
@@ -423,6 +438,10 @@ class FiberBlock {
   unsigned long long polls_ = 0;
   char block_sync_ = 0, launch_sync_ = 0;  // addresses for the happens-before annotations of the race check
   std::vector<char> warp_sync_;
+  std::vector<unsigned> wmask_, shc_;
+  std::vector<double> shv_;
+  unsigned *wm_ = nullptr, *sc_ = nullptr;
+  double* sv_ = nullptr;
   Context* fib_ = nullptr;
   ThreadCtx* tc_ = nullptr;
   unsigned char* st_ = nullptr;
@@ -461,6 +480,7 @@ void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& b
       for (unsigned t = 0; t < nt; ++t) {
         ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
         ctx.bid = block_id(b), ctx.bdim = block, ctx.gdim = grid, ctx.dyn_smem = smem.data(), ctx.in_block = false;
+        ctx.dyn_bytes = smem_doubles * sizeof(double);
         body();
       }
     return;
@@ -470,7 +490,8 @@ void launch(dim3 grid, dim3 block, bool has_barrier, size_t smem_bytes, Body&& b
   auto work = [&](unsigned w, unsigned stride) {
     std::vector<double> smem(smem_doubles);
     FiberBlock fb(nt);
-    for (unsigned b = w; b < nblocks; b += stride) fb.run(body, block_id(b), block, grid, smem.data());
+    for (unsigned b = w; b < nblocks; b += stride)
+      fb.run(body, block_id(b), block, grid, smem.data(), smem_doubles * sizeof(double));
   };
   if (workers <= 1) {
     work(0, 1);
@@ -525,14 +546,23 @@ void __stcs(T* p, T v) {
   *p = v;
 }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
-inline double __shfl_sync(unsigned, double, int) {
-  std::fprintf(stderr, "host emulation: partial-warp shuffles are not emulated (potrf_tile_kernel, COCONS_POTRF=1)\n");
-  std::abort();
-}
+inline double __shfl_sync(unsigned mask, double v, int src) { return emul_block()->shuffle(mask, v, src); }
 // offset of a shared-memory object inside the launch's dynamic shared memory (what the 32-bit shared-window
 // address is used for in the kernels: mbarrier and bulk-copy operands)
+// ... or, for an object in a static __shared__ array (the mbarriers of potrf_tile_kernel), a handle: bit 31 + an index
+// into a per-thread table of such objects.  No arithmetic is done on those handles by the kernels.
+namespace emul {
+inline thread_local std::vector<const void*> static_shared_objects;
+}
 inline size_t __cvta_generic_to_shared(const void* p) {
-  return (size_t)(static_cast<const char*>(p) - static_cast<const char*>(emul::ctx.dyn_smem));
+  const char* base = static_cast<const char*>(emul::ctx.dyn_smem);
+  const char* q = static_cast<const char*>(p);
+  if (base && q >= base && q < base + emul::ctx.dyn_bytes) return (size_t)(q - base);
+  auto& tab = emul::static_shared_objects;
+  for (size_t i = 0; i < tab.size(); ++i)
+    if (tab[i] == p) return 0x80000000u | i;
+  tab.push_back(p);
+  return 0x80000000u | (tab.size() - 1);
 }
 
 // ---- stand-ins for the inline-PTX helper functions of the kernels (tests/host_emul/build.py replaces the body of a
@@ -558,7 +588,11 @@ struct MBar {
   uint32_t phase : 1;
 };
 static_assert(sizeof(MBar) == 8, "an mbarrier is one 64-bit word");
-EMUL_NO_TSAN inline MBar* mbar_at(uint32_t off) { return reinterpret_cast<MBar*>(static_cast<char*>(ctx.dyn_smem) + off); }
+EMUL_NO_TSAN inline MBar* mbar_at(uint32_t off) {
+  if (off & 0x80000000u)
+    return reinterpret_cast<MBar*>(const_cast<void*>(static_shared_objects[off & 0x7FFFFFFFu]));
+  return reinterpret_cast<MBar*>(static_cast<char*>(ctx.dyn_smem) + off);
+}
 EMUL_NO_TSAN inline void mbar_check(MBar* m) {
   if (m->pending == 0 && m->tx == 0) m->phase ^= 1, m->pending = m->expected;
 }

@@ -245,6 +245,15 @@ int emu_potrf_tile(double* A, int64_t ld, double* winv, int first_index) {
   return info;
 }
 
+// the register-resident column-sweep variant of the tile kernel (K3, COCONS_POTRF=1): half-warp shuffles for the
+// pivot, three mbarriers in static shared memory for the one-step-ahead column pipeline
+int emu_potrf_tile_sweep(double* A, int64_t ld, double* winv, int first_index) {
+  int info = 0;
+  int* pinfo = &info;
+  emul::launch(dim3(1), dim3(256), true, 0, [&] { potrf_tile_kernel(A, ld, winv, pinfo, first_index); });
+  return info;
+}
+
 // launch_gemm_nt: mode 0  C -= A B^T (128 x 64 tiles, optionally only the tiles on or below the diagonal),
 //                 mode 1  C  = A B^T (128 x 128 tiles)
 void emu_gemm_nt(int mode, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,

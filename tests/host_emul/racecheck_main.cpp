@@ -103,6 +103,10 @@ int main(int argc, char** argv) {
     std::vector<double> Y = random_matrix(n, 2), G(4);
     emu_gram(Y.data(), n - 5, n, 2, G.data());
     if (!(emu_logdet(S.data(), n - 5, n) == emu_logdet(S.data(), n - 5, n))) return 4;
+    {  // the column-sweep variant of the tile kernel (K3, COCONS_POTRF=1)
+      std::vector<double> T = spd(128), Wt((size_t)128 * 128);
+      if (emu_potrf_tile_sweep(T.data(), 128, Wt.data(), 0) != 0) return 4;
+    }
     std::printf("cholesky / solves ok\n");
   }
   // 4. pairwise assembly (general Bessel branch): square with symmetrisation, cross-covariance

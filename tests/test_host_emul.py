@@ -388,6 +388,15 @@ def test_diagonal_tile_kernel_on_the_host(emu):
     bad[70, 70] = -1.0  # leading minor of order 71 is not positive definite
     A = np.asfortranarray(bad)
     assert emu.emu_potrf_tile(_p(A), 128, _p(W), 1000) == 1000 + 71
+    # K3, the register-resident column sweep kept behind COCONS_POTRF=1 (half-warp shuffles, mbarriers in static
+    # shared memory, one column ahead): same outputs
+    A = np.asfortranarray(S.copy())
+    W = np.full((128, 128), np.nan, order="F")
+    assert emu.emu_potrf_tile_sweep(_p(A), 128, _p(W), 0) == 0
+    assert np.max(np.abs(A - L)) < 1e-14 and np.array_equal(np.triu(A, 1), np.zeros((128, 128)))
+    assert np.max(np.abs(W - np.linalg.inv(L))) < 1e-13 and np.array_equal(np.triu(W, 1), np.zeros((128, 128)))
+    A = np.asfortranarray(bad)
+    assert emu.emu_potrf_tile_sweep(_p(A), 128, _p(W), 1000) == 1000 + 71
 
 
 @pytest.mark.parametrize("mode,M,N,K,lower", [(0, 384, 256, 48, 0), (0, 384, 384, 144, 1), (1, 256, 128, 128, 0)])
