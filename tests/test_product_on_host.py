@@ -144,3 +144,13 @@ def test_more_of_the_gpu_suite_at_small_sizes(product_on_host, datasets):
     for n in (100, 128, 517):
         test_gpu_n2ll.test_factor_reconstructs_sigma(n, datasets)
     test_gpu_predict_sim.test_predict_after_fixed_smoothness_factor(datasets)
+
+
+def test_measurement_helper_runs(product_on_host):
+    """cocons_bench_syrk (the stand-alone trailing-update timing of bench.py / tools): argument checks and one run"""
+    import ctypes
+    ms = ctypes.c_double(-1.0)
+    L = _lib.lib()
+    assert L.cocons_bench_syrk(0, 256, 32, 1, ctypes.byref(ms)) == 0 and ms.value >= 0.0
+    assert L.cocons_bench_syrk(0, 200, 32, 1, ctypes.byref(ms)) < 0  # n must be a multiple of 128
+    assert b"multiple of 128" in L.cocons_last_error()
